@@ -250,6 +250,7 @@ int orc_merkle_commit(const u32* const* mats, const u64* heights, const u64* wid
 /* MerkleTreeMmcs::verify_batch.  rows[k] are the opened rows (widths[k] elems), heights as committed.
  * path: depth x 8.  returns 1 if the recomputed root equals `root`. */
 int orc_merkle_verify(const u32* const* rows, const u64* heights, const u64* widths, u32 k, const u32* path, u32 depth, u64 index, const u32* root) {
+    if (!k) return 0;
     u32* order = malloc(sizeof(u32) * k);
     for (u32 i = 0; i < k; i++) order[i] = i;
     for (u32 i = 1; i < k; i++) {

@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and the host mirror of the Plonky3
+traits, must be bit-identical to the oracle and to the golden vectors mined from the reference's fixture."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+P = O.P
+
+
+@pytest.fixture(scope="module")
+def z():
+    import zkvm_prover_b200 as zz
+    return zz
+
+
+@pytest.fixture(scope="module")
+def ctx(z):
+    return z.default_context(0)
+
+
+def rnd(shape, seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, P, shape, dtype=np.uint64).astype(np.uint32)
+
+
+def u32(x):
+    return np.asarray(x, dtype=np.uint32)
+
+
+# ------------------------------------------------------------------------------------------ K3 permutation
+def test_permute_matches_oracle(z, ctx):
+    st = rnd((5000, 16), 1)
+    st[0] = 0
+    st[1] = P - 1
+    st[2] = O.to_monty(np.arange(16))
+    perm = z.Poseidon2BabyBear16(ctx)
+    got = perm.permute(st)
+    assert np.array_equal(got, O.permute(st))
+    assert O.from_monty(got[2]).tolist()[:4] == [1906786279, 1737026427, 1959749225, 700325316]
+    # in-library cross-check: plain formulation == optimised formulation
+    d = C.c_void_p()
+    ctx.check(ctx.lib.b200zk_dev_alloc(ctx.h, st.nbytes, C.byref(d)))
+    ctx.check(ctx.lib.b200zk_dev_upload(ctx.h, d, st.ctypes.data, st.nbytes))
+    ctx.check(ctx.lib.b200zk_poseidon2_permute_plain_dev(ctx.h, d, st.shape[0]))
+    out = np.empty_like(st)
+    ctx.check(ctx.lib.b200zk_dev_download(ctx.h, out.ctypes.data, d, st.nbytes))
+    ctx.lib.b200zk_dev_free(ctx.h, d)
+    assert np.array_equal(out, got)
+    assert perm.permute(np.zeros((0, 16), np.uint32)).size == 0  # empty input
+
+
+# ------------------------------------------------------------------------------------------ K4/K5 hashing
+@pytest.mark.parametrize("w", [1, 5, 7, 8, 9, 16, 23, 64, 256, 398])
+def test_hash_rows_matches_oracle(z, ctx, w):
+    m = rnd((300, w), w)
+    assert np.array_equal(z.PaddingFreeSponge(z.Poseidon2BabyBear16(ctx)).hash_rows(m), O.hash_rows(m))
+
+
+def test_hasher_trait_surface(z, ctx, kats):
+    h = z.PaddingFreeSponge(z.Poseidon2BabyBear16(ctx))
+    k = kats["b3_single_matrix"]
+    assert np.array_equal(h.hash_slice(k["row"]), u32(k["leaf_digest"]))  # reference fixture leaf (B-3)
+    assert np.array_equal(h.hash_iter(iter(k["row"])), u32(k["leaf_digest"]))
+    assert np.array_equal(h.hash_iter_slices([k["row"][:4], k["row"][4:]]), u32(k["leaf_digest"]))
+    assert np.array_equal(h.hash_item(5), O.hash_rows(u32([[5]]))[0])
+    assert np.array_equal(h.hash_slice([]), np.zeros(8, np.uint32))
+    c = z.TruncatedPermutation(z.Poseidon2BabyBear16(ctx))
+    pairs = rnd((100, 16), 3)
+    assert np.array_equal(c.compress(pairs), O.compress_pairs(pairs))
+    assert np.array_equal(c.compress(pairs[0].reshape(2, 8)), O.compress_pairs(pairs[:1])[0])
+
+
+# ------------------------------------------------------------------------------------------ MerkleTreeMmcs
+SHAPES = [
+    [(8, 3)],
+    [(1, 5)],
+    [(2, 16), (1, 1)],
+    [(16, 9), (16, 8), (4, 5), (1, 2)],
+    [(4, 17), (32, 1), (8, 8), (8, 7)],
+    [(4096, 8)],                      # exercises the single-CTA top-of-tree kernel + fast path
+    [(8192, 24), (8192, 5), (2048, 3), (2, 40)],
+    [(64, 256), (64, 64)],            # fast path with two matrices in one sponge
+]
+
+
+@pytest.mark.parametrize("shapes", SHAPES)
+def test_merkle_commit_open_verify(z, ctx, shapes):
+    mats = [rnd(s, 7 + i + s[0]) for i, s in enumerate(shapes)]
+    mmcs = z.MerkleTreeMmcs(ctx)
+    root, pd = mmcs.commit(mats)
+    oroot, olayers = O.merkle_commit(mats)
+    assert np.array_equal(root, oroot)
+    for i, l in enumerate(olayers):
+        assert np.array_equal(pd.layer(i), l), f"layer {i}"
+    max_h = max(s[0] for s in shapes)
+    dims = [(s[1], s[0]) for s in shapes]
+    for idx in sorted(set([0, 1 % max_h, max_h // 2, max_h - 1, (max_h * 5) // 7])):
+        rows, path = mmcs.open_batch(idx, pd)
+        orows, opath = O.merkle_open(mats, olayers, idx)
+        assert all(np.array_equal(a, b) for a, b in zip(rows, orows)) and np.array_equal(path, opath)
+        assert O.merkle_verify(rows, [s[0] for s in shapes], path, idx, root)
+        mmcs.verify_batch(root, dims, idx, rows, path)
+        bad = [r.copy() for r in rows]
+        bad[0][0] ^= 1
+        with pytest.raises(ValueError):
+            mmcs.verify_batch(root, dims, idx, bad, path)
+    assert [m.rows for m in mmcs.get_matrices(pd)] == [s[0] for s in shapes]
+    assert np.array_equal(mmcs.get_matrices(pd)[0].to_host(), mats[0])
+
+
+def test_merkle_fixture_openings_verify_on_device(z, ctx, kats):
+    """B-3 / B-3b: openings produced by the real prover verify against its commitments on the device."""
+    mmcs = z.MerkleTreeMmcs(ctx)
+    k = kats["b3_single_matrix"]
+    mmcs.verify_batch(k["root"], [(len(k["row"]), k["height"])], k["index"], [k["row"]], k["path"])
+    for b in kats["b3b_mixed_height"]:
+        dims = [(len(r), h) for r, h in zip(b["rows"], b["heights"])]
+        mmcs.verify_batch(b["root"], dims, b["index"], b["rows"], b["path"])
+        with pytest.raises(ValueError):
+            mmcs.verify_batch(b["root"], dims, b["index"] ^ 2, b["rows"], b["path"])
+
+
+def test_merkle_errors(z, ctx):
+    mmcs = z.MerkleTreeMmcs(ctx)
+    with pytest.raises(z.B200zkError) as e:
+        mmcs.commit([np.zeros((6, 3), np.uint32)])
+    assert e.value.code == -3
+    with pytest.raises(ValueError):
+        mmcs.commit([])
+    root, pd = mmcs.commit([rnd((8, 2), 1)])
+    with pytest.raises(z.B200zkError) as e:
+        mmcs.open_batch(8, pd)
+    assert e.value.code == -4
+
+
+# ------------------------------------------------------------------------------------------ K2 NTT / LDE
+@pytest.mark.parametrize("n,w", [(0, 3), (1, 1), (2, 5), (3, 4), (5, 32), (9, 36), (10, 8), (11, 3), (13, 64), (14, 4), (18, 4), (19, 4), (21, 4)])
+def test_dft_batch_matches_oracle(z, ctx, n, w):
+    a = rnd((1 << n, w), 100 + n)
+    dft = z.B200Dft(ctx)
+    shift = int(O.to_monty([31])[0])
+    assert np.array_equal(dft.dft_batch(a).to_host(), O.dft_batch(a))
+    assert np.array_equal(dft.coset_dft_batch(a, shift).to_host(), O.dft_batch(a, shift=shift))
+    assert np.array_equal(dft.idft_batch(a).to_host(), O.dft_batch(a, inverse=True))
+    assert np.array_equal(dft.coset_idft_batch(a, shift).to_host(), O.dft_batch(a, shift=shift, inverse=True))
+    if n <= 8:
+        assert np.array_equal(dft.dft_batch(a).to_host(), O.naive_dft(a))  # the definition (NaiveDft)
+    m = ctx.upload(a)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.b200zk_dft_batch(ctx.h, m.h, shift, 0, 1, C.byref(h)))
+    br = z.DeviceMatrix(ctx, h, True).to_host()
+    assert np.array_equal(br, O.dft_batch(a, shift=shift, bitrev_out=True))
+
+
+def test_dft_single_vector_and_roundtrip(z, ctx):
+    dft = z.B200Dft(ctx)
+    v = rnd(256, 5)
+    assert np.array_equal(dft.idft(dft.dft(v)), v)
+    assert np.array_equal(dft.dft(v), O.dft_batch(v.reshape(-1, 1)).reshape(-1))
+
+
+def test_coset_lde_fixture_kat(z, ctx, kats):
+    """B-6: an 8x5 LDE block of the reference's own proof (shift 31, bit-reversed rows)."""
+    k = kats["b6_coset_lde"]
+    got = z.B200Dft(ctx).coset_lde_batch(u32(k["trace"]), k["added_bits"], k["shift"], bit_reversed=True).to_host()
+    assert np.array_equal(got, u32(k["lde_bitrev_rows"]))
+
+
+@pytest.mark.parametrize("n,w,b", [(0, 4, 1), (1, 3, 1), (3, 5, 2), (6, 32, 1), (9, 8, 1), (10, 36, 2), (12, 64, 1), (12, 7, 0), (13, 4, 3), (17, 8, 1), (19, 4, 1), (20, 4, 1)])
+def test_coset_lde_matches_oracle(z, ctx, n, w, b):
+    ev = rnd((1 << n, w), 200 + n + b)
+    shift = int(O.to_monty([31])[0])
+    dft = z.B200Dft(ctx)
+    assert np.array_equal(dft.coset_lde_batch(ev, b, shift, bit_reversed=True).to_host(), O.coset_lde_batch(ev, b, shift, bitrev_out=True))
+    if n <= 13:
+        assert np.array_equal(dft.coset_lde_batch(ev, b, shift).to_host(), O.coset_lde_batch(ev, b, shift, bitrev_out=False))
+        nat1 = dft.lde_batch(ev, b).to_host()
+        assert np.array_equal(nat1[:: 1 << b], ev)  # shift 1: the extension contains the original evaluations
+
+
+def test_dft_errors(z, ctx):
+    dft = z.B200Dft(ctx)
+    with pytest.raises(z.B200zkError) as e:
+        dft.dft_batch(np.zeros((6, 2), np.uint32))
+    assert e.value.code == -3
+    with pytest.raises(z.B200zkError) as e:
+        dft.coset_lde_batch(np.zeros((4, 2), np.uint32), 30, O.MONTY_ONE)
+    assert e.value.code == -3
+    with pytest.raises(z.B200zkError) as e:
+        dft.coset_dft_batch(np.zeros((4, 2), np.uint32), 0)
+    assert e.value.code == -4
+
+
+# ------------------------------------------------------------------------------------------ challenger
+def test_challenger_matches_oracle(z, ctx):
+    rng = np.random.default_rng(6)
+    c, o = z.DuplexChallenger(ctx), O.Challenger()
+    for _ in range(40):
+        if rng.integers(0, 2):
+            v = rnd(int(rng.integers(1, 20)), int(rng.integers(0, 1 << 30)))
+            c.observe(v)
+            o.observe(v)
+        else:
+            assert c.sample() == o.sample()
+    assert np.array_equal(c.sample_algebra_element(), o.sample_ext())
+    assert c.sample_bits(10) == o.sample_bits(10)
+    assert np.array_equal(c.state(), o.state())
+    assert c.grind(12) == o.grind(12)
+    assert c.sample() == o.sample()
+    assert np.array_equal(c.state(), o.state())
+
+
+# ------------------------------------------------------------------------------------------ K6 FRI
+def test_fri_fixture_last_layer(z, ctx, kats):
+    """B-5: last commit-phase layer of the reference proof: root, and fold with the implied beta."""
+    k = kats["b5_fri_last_layer"]
+    layer = u32(k["layer_bitrev"])
+    root, pd = z.ExtensionMmcs(z.MerkleTreeMmcs(ctx)).commit_matrix(layer.reshape(4, 2, 4))
+    assert np.array_equal(root, u32(k["root"]))
+    folded = z.fold_matrix(u32(k["beta"]), layer, ctx)
+    assert all(np.array_equal(f, u32(k["folded_const"])) for f in folded)
+
+
+@pytest.mark.parametrize("ln", [1, 2, 5, 10, 14])
+def test_fold_matrix_matches_oracle(z, ctx, ln):
+    v = rnd((1 << ln, 4), 300 + ln)
+    beta = rnd(4, 301 + ln)
+    assert np.array_equal(z.fold_matrix(beta, v, ctx), O.fri_fold(v, beta))
+    add = rnd((1 << (ln - 1), 4), 7)
+    exp = O.fri_fold(v, beta).astype(np.uint64) + add
+    exp = (exp % P).astype(np.uint32)
+    assert np.array_equal(z.fold_matrix(beta, v, ctx, add=add), exp)
+
+
+@pytest.mark.parametrize("ln,lb,lf", [(6, 1, 0), (12, 1, 0), (12, 2, 2), (15, 1, 1), (3, 1, 0)])
+def test_commit_phase_matches_oracle(z, ctx, ln, lb, lf):
+    vec = rnd((1 << ln, 4), 400 + ln)
+    seed = rnd(11, 401)
+    cfg = z.FriConfig(log_blowup=lb, log_final_poly_len=lf)
+    # device challenger drives the betas
+    c, o = z.DuplexChallenger(ctx), O.Challenger()
+    c.observe(seed)
+    o.observe(seed)
+    res = z.commit_phase(cfg, [vec], c, ctx)
+    oroots, obetas, ofin = O.fri_commit_phase(vec, lb, lf, challenger=o)
+    assert np.array_equal(res.commits, oroots) and np.array_equal(res.betas, obetas) and np.array_equal(res.final_poly, ofin)
+    assert np.array_equal(c.state(), o.state())
+    # per-round trees open and verify (query phase needs them)
+    if len(res.data):
+        mmcs = z.MerkleTreeMmcs(ctx)
+        t0 = res.data[0]
+        rows, path = mmcs.open_batch(3 % (1 << (ln - 1)), t0)
+        assert np.array_equal(rows[0] if rows else None, vec.reshape(-1, 8)[3 % (1 << (ln - 1))]) if rows else True
+    # forced betas reproduce the same transcript
+    res2 = z.commit_phase(cfg, [vec], None, ctx, betas=obetas if len(obetas) else np.zeros((1, 4), np.uint32))
+    assert np.array_equal(res2.commits, oroots) and np.array_equal(res2.final_poly, ofin)
+
+
+def test_commit_phase_low_degree_and_rollin(z, ctx):
+    ev = rnd((512, 4), 9)
+    code = O.coset_lde_batch(ev, 1, O.MONTY_ONE, bitrev_out=True)  # 1024 EF4, an honest codeword
+    betas = rnd((10, 4), 10)
+    res = z.commit_phase(z.FriConfig(1, 0), [code], None, ctx, betas=betas)
+    assert len(res.commits) == 9 and np.array_equal(res.final_poly[0], res.final_poly[1])
+    # roll-in: a second, shorter input is added when the folded length reaches its length
+    small = rnd((256, 4), 11)
+    res2 = z.commit_phase(z.FriConfig(1, 0), [code, small], None, ctx, betas=betas)
+    f = code
+    for r in range(9):
+        root, _ = O.merkle_commit([f.reshape(-1, 8)])
+        assert np.array_equal(res2.commits[r], root)
+        f = O.fri_fold(f, betas[r])
+        if f.shape[0] == 256:
+            f = ((f.astype(np.uint64) + small) % P).astype(np.uint32)
+    assert np.array_equal(res2.final_poly, f)
+
+
+# ------------------------------------------------------------------------------------------ TwoAdicFriPcs::commit
+def test_pcs_commit_lde_plus_mmcs(z, ctx):
+    traces = [rnd((1 << 10, 24), 1), rnd((1 << 10, 5), 2), rnd((1 << 6, 9), 3), rnd((2, 5), 4)]
+    pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=2), ctx)
+    root, pd = pcs.commit(traces)
+    shift = int(O.to_monty([31])[0])
+    ldes = [O.coset_lde_batch(t, 2, shift, bitrev_out=True) for t in traces]
+    oroot, _ = O.merkle_commit(ldes)
+    assert np.array_equal(root, oroot)
+    for i, l in enumerate(ldes):
+        assert np.array_equal(pcs.get_evaluations_on_domain(pd, i).to_host(), l)
+    rows, path = pcs.mmcs.open_batch(1234, pd)
+    pcs.mmcs.verify_batch(root, [(l.shape[1], l.shape[0]) for l in ldes], 1234, rows, path)
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_lde_2pow20_x64_checksum_vs_oracle(z, ctx):
+    """BASELINE config 2^20 x 64, log_blowup 1: device-generated input, order-independent checksum of the
+    whole 2^21 x 64 output against the oracle's."""
+    n, w = 20, 64
+    seed = 0xB2000000 + (n << 16) + w
+    m = ctx.alloc(1 << n, w).fill(seed)
+    host = O.fill((1 << n) * w, seed).reshape(1 << n, w)
+    assert m.checksum() == O.checksum(host)
+    shift = int(O.to_monty([31])[0])
+    out = z.B200Dft(ctx).coset_lde_batch(m, 1, shift, bit_reversed=True)
+    exp = O.coset_lde_batch(host, 1, shift, bitrev_out=True)
+    assert out.checksum() == O.checksum(exp)
+    assert np.array_equal(out.rows_to_host(12345, 3), exp[12345:12348])
+
+
+def test_lde_commit_large_properties(z, ctx):
+    """2^22 x 64: (i) LDE with shift 1 contains the input at even bit-reversed positions, (ii) the commit of
+    the LDE opens and verifies, (iii) Horner spot checks of the oracle's coefficients."""
+    n, w = 22, 64
+    m = ctx.alloc(1 << n, w).fill(77)
+    dft = z.B200Dft(ctx)
+    lde = dft.coset_lde_batch(m, 1, O.MONTY_ONE, bit_reversed=True)
+    # physical row j holds logical row bitrev(j); logical even rows 2i == input row i  => physical rows j < N hold input row bitrev_n(j)
+    for j in (0, 1, 5, 99999, (1 << n) - 1):
+        i = int('{:0{w}b}'.format(j, w=n)[::-1], 2)
+        assert np.array_equal(lde.rows_to_host(j, 1), m.rows_to_host(i, 1))
+    mmcs = z.MerkleTreeMmcs(ctx)
+    root, pd = mmcs.commit([lde])
+    idx = 3141592
+    rows, path = mmcs.open_batch(idx, pd)
+    assert O.merkle_verify(rows, [1 << (n + 1)], path, idx, root)

@@ -1,0 +1,1060 @@
+// C ABI of libb200zk (see include/b200zk.h).  Host-side orchestration only: argument checking, device
+// memory, pass planning and kernel launches on the context's stream.  No CPU arithmetic path exists here:
+// every field operation on user data happens in the kernels of ntt.cuh / merkle.cuh / fri.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zk.h"
+#include "fri.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+namespace {
+
+constexpr int MAX_LOG = 27;
+constexpr int KMAX_SMALL = 9;   // 64 KB tile: two CTAs per SM
+constexpr int KMAX_BIG = 10;    // 128 KB tile: used when it saves a whole pass (n = 19, 20)
+constexpr uint32_t TOP_LAYER = 2048;  // digest layers at or below this size are finished by one CTA
+
+}  // namespace
+
+struct b200zk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    uint32_t* tw_local[2][KMAX_BIG + 1] = {};
+    uint32_t* tw_lo[MAX_LOG + 1] = {};
+    uint32_t* tw_hi[MAX_LOG + 1] = {};
+    uint32_t* tab = nullptr;  // scratch for per-call power tables (stream ordered reuse)
+    size_t tab_words = 0;
+    uint32_t* d_small = nullptr;  // 64 KB of small device scratch (roots, betas, flags)
+    int max_smem_optin = 0;
+};
+struct b200zk_mat {
+    uint32_t* d = nullptr;
+    uint64_t rows = 0;
+    uint32_t width = 0;
+    bool owned = false;
+};
+struct b200zk_tree {
+    std::vector<b200zk_mat*> mats;  // original order
+    bool owns_mats = false;
+    uint64_t max_h = 0;
+    uint32_t depth = 0;
+    uint64_t total_width = 0;
+    uint32_t* d_digests = nullptr;  // layer 0 | layer 1 | ... | root
+    std::vector<uint64_t> layer_off;  // in digests
+    mk::OpenMat* d_open = nullptr;
+};
+struct b200zk_chal {
+    fri::ChalState* d = nullptr;
+};
+
+namespace {
+
+int fail(b200zk_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? B200ZK_ERR_OOM : B200ZK_ERR_CUDA,       \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+        }                                                                                              \
+    } while (0)
+#define LAUNCHED()                                                                                     \
+    do {                                                                                               \
+        ctx->launches++;                                                                               \
+        CU(cudaGetLastError());                                                                        \
+    } while (0)
+#define TRY(call)                                                                                      \
+    do {                                                                                               \
+        int r_ = (call);                                                                               \
+        if (r_ != B200ZK_OK) return r_;                                                                \
+    } while (0)
+
+inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+inline int log2u(uint64_t x) {
+    int l = 0;
+    while ((1ull << l) < x) l++;
+    return l;
+}
+
+int dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
+    *out = nullptr;
+    if (!bytes) bytes = 16;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, B200ZK_ERR_OOM, "cudaMalloc(" + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    return B200ZK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- twiddles
+int ensure_tab(b200zk_ctx* ctx, size_t words) {
+    if (ctx->tab_words >= words) return B200ZK_OK;
+    if (ctx->tab) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->tab);
+        ctx->tab = nullptr;
+        ctx->tab_words = 0;
+    }
+    TRY(dev_alloc(ctx, words * 4, (void**)&ctx->tab));
+    ctx->tab_words = words;
+    return B200ZK_OK;
+}
+
+int pow_tables(b200zk_ctx* ctx, uint32_t* lo, uint32_t* hi, uint32_t base, uint32_t scale, uint64_t n_entries) {
+    uint32_t n_lo = (uint32_t)std::min<uint64_t>(n_entries, 1u << ntt::LO_BITS);
+    uint32_t n_hi = (uint32_t)std::max<uint64_t>(n_entries >> ntt::LO_BITS, 1);
+    uint32_t m = std::max(n_lo, n_hi);
+    ntt::pow_table_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(lo, hi, base, scale, n_lo, n_hi);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+inline size_t lo_words(uint64_t n_entries) { return (size_t)std::min<uint64_t>(n_entries, 1u << ntt::LO_BITS); }
+inline size_t hi_words(uint64_t n_entries) { return (size_t)std::max<uint64_t>(n_entries >> ntt::LO_BITS, 1); }
+
+int ensure_roots(b200zk_ctx* ctx, int n) {
+    if (ctx->tw_lo[n]) return B200ZK_OK;
+    uint64_t N = 1ull << n;
+    TRY(dev_alloc(ctx, lo_words(N) * 4, (void**)&ctx->tw_lo[n]));
+    TRY(dev_alloc(ctx, hi_words(N) * 4, (void**)&ctx->tw_hi[n]));
+    return pow_tables(ctx, ctx->tw_lo[n], ctx->tw_hi[n], bb::two_adic_generator(n), bb::ONE, N);
+}
+int ensure_local(b200zk_ctx* ctx, int inverse, int K) {
+    if (ctx->tw_local[inverse][K]) return B200ZK_OK;
+    uint32_t half = K ? (1u << (K - 1)) : 1;
+    TRY(dev_alloc(ctx, std::max<uint32_t>(half, 4096u + 1) * 4, (void**)&ctx->tw_local[inverse][K]));
+    uint32_t g = bb::two_adic_generator(K);
+    if (inverse) g = bb::inv(g);
+    // reuse the two-level generator with every entry in `lo` (half <= 512 < 4096); hi gets one dummy entry
+    ntt::pow_table_kernel<<<(half + 255) / 256, 256, 0, ctx->stream>>>(ctx->tw_local[inverse][K], ctx->tw_local[inverse][K] + 4096, g, bb::ONE, half, 1);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+
+// split n stages into passes
+std::vector<int> make_plan(int n) {
+    std::vector<int> plan;
+    if (n <= 0) return plan;
+    int kmax = (n > 2 * KMAX_SMALL && n <= 2 * KMAX_BIG) ? KMAX_BIG : KMAX_SMALL;
+    int m = (n + kmax - 1) / kmax;
+    for (int i = 0; i < m; i++) plan.push_back(n / m + (i < n % m ? 1 : 0));
+    return plan;
+}
+
+struct Scale {
+    const uint32_t* lo = nullptr;
+    const uint32_t* hi = nullptr;
+};
+
+// n-stage DIF over `rows = 2^n` rows.  src -> dst (first pass), then in place on dst; when out_natural the
+// last pass scatters into dst_final (which must not alias its source).
+int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t* dst_final, int n, uint32_t width, int inverse, Scale pre,
+                  Scale post, int out_natural) {
+    std::vector<int> plan = make_plan(n);
+    TRY(ensure_roots(ctx, n));
+    const int vec = (width % 4 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)work % 16 == 0) && ((uintptr_t)dst_final % 16 == 0)) ? 4 : 1;
+    const uint32_t col_tiles = (width + ntt::TILE_COLS - 1) / ntt::TILE_COLS;
+    int s0 = 0;
+    for (size_t i = 0; i < plan.size(); i++) {
+        const int K = plan[i];
+        const bool first = i == 0, last = i + 1 == plan.size();
+        TRY(ensure_local(ctx, inverse, K));
+        ntt::PassParams p;
+        p.in = first ? src : work;
+        p.out = last ? dst_final : work;
+        p.width = width;
+        p.n = n;
+        p.s0 = s0;
+        p.K = K;
+        p.inverse = inverse;
+        p.tw_local = ctx->tw_local[inverse][K];
+        p.tw_lo = ctx->tw_lo[n];
+        p.tw_hi = ctx->tw_hi[n];
+        p.pre_lo = first ? pre.lo : nullptr;
+        p.pre_hi = first ? pre.hi : nullptr;
+        p.post_lo = last ? post.lo : nullptr;
+        p.post_hi = last ? post.hi : nullptr;
+        p.out_natural = last ? out_natural : 0;
+        const uint64_t R = 1ull << K;
+        const size_t smem = (R * ntt::TILE_COLS + std::max<uint64_t>(R / 2, 1) + R) * 4;
+        const uint64_t blocks = ((1ull << n) >> K) * col_tiles;
+        if (blocks > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
+        if (vec == 4) {
+            CU(cudaFuncSetAttribute(ntt::pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ntt::pass_kernel<4><<<(uint32_t)blocks, ntt::THREADS, smem, ctx->stream>>>(p);
+        } else {
+            CU(cudaFuncSetAttribute(ntt::pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ntt::pass_kernel<1><<<(uint32_t)blocks, ntt::THREADS, smem, ctx->stream>>>(p);
+        }
+        LAUNCHED();
+        s0 += K;
+    }
+    return B200ZK_OK;
+}
+
+int check_mat(b200zk_ctx* ctx, const b200zk_mat* m) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!m || !m->d) return fail(ctx, B200ZK_ERR_ARG, "null matrix");
+    return B200ZK_OK;
+}
+
+__global__ void fill_kernel(uint32_t* out, uint64_t n, uint64_t seed) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (uint32_t)(bb::splitmix64(seed ^ i) % bb::P);
+}
+__global__ void checksum_kernel(const uint32_t* __restrict__ v, uint64_t n, unsigned long long* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (; i < n; i += stride) acc += bb::splitmix64(i ^ ((uint64_t)v[i] << 32));
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+__global__ void replicate_row_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t rows, uint32_t width) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * width) out[i] = in[i % width];
+}
+
+}  // namespace
+
+// ================================================================================================ context
+extern "C" {
+
+const char* b200zk_version(void) { return "b200zk 0.1 (sm_100a)"; }
+
+int b200zk_ctx_create(int device, b200zk_ctx** out) {
+    if (!out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return B200ZK_ERR_CUDA;  // no CUDA device: there is no CPU fallback
+    }
+    b200zk_ctx* ctx = new (std::nothrow) b200zk_ctx();
+    if (!ctx) return B200ZK_ERR_OOM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return B200ZK_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (cudaMalloc((void**)&ctx->d_small, 65536) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return B200ZK_ERR_OOM;
+    }
+    *out = ctx;
+    return B200ZK_OK;
+}
+
+void b200zk_ctx_destroy(b200zk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& dir : ctx->tw_local)
+        for (auto& p : dir) cudaFree(p);
+    for (auto& p : ctx->tw_lo) cudaFree(p);
+    for (auto& p : ctx->tw_hi) cudaFree(p);
+    cudaFree(ctx->tab);
+    cudaFree(ctx->d_small);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* b200zk_last_error(const b200zk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int b200zk_ctx_sync(b200zk_ctx* ctx) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+void* b200zk_ctx_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t b200zk_kernel_launches(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ================================================================================================ matrices
+int b200zk_mat_alloc(b200zk_ctx* ctx, uint64_t rows, uint32_t width, b200zk_mat** out) {
+    if (!ctx || !out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    if (!rows || !width) return fail(ctx, B200ZK_ERR_SHAPE, "empty matrix");
+    CU(cudaSetDevice(ctx->device));
+    b200zk_mat* m = new (std::nothrow) b200zk_mat();
+    if (!m) return B200ZK_ERR_OOM;
+    int r = dev_alloc(ctx, rows * width * 4, (void**)&m->d);
+    if (r) {
+        delete m;
+        return r;
+    }
+    m->rows = rows;
+    m->width = width;
+    m->owned = true;
+    *out = m;
+    return B200ZK_OK;
+}
+int b200zk_mat_upload_into(b200zk_ctx* ctx, const uint32_t* h, b200zk_mat* dst) {
+    TRY(check_mat(ctx, dst));
+    if (!h) return fail(ctx, B200ZK_ERR_ARG, "null host pointer");
+    CU(cudaMemcpyAsync(dst->d, h, dst->rows * dst->width * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return B200ZK_OK;
+}
+int b200zk_mat_upload(b200zk_ctx* ctx, const uint32_t* h, uint64_t rows, uint32_t width, b200zk_mat** out) {
+    if (!h) return fail(ctx, B200ZK_ERR_ARG, "null host pointer");
+    TRY(b200zk_mat_alloc(ctx, rows, width, out));
+    int r = b200zk_mat_upload_into(ctx, h, *out);
+    if (r == B200ZK_OK) r = b200zk_ctx_sync(ctx);
+    if (r) {
+        b200zk_mat_free(ctx, *out);
+        *out = nullptr;
+    }
+    return r;
+}
+int b200zk_mat_wrap(b200zk_ctx* ctx, uint32_t* d, uint64_t rows, uint32_t width, b200zk_mat** out) {
+    if (!ctx || !out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    if (!d) return fail(ctx, B200ZK_ERR_ARG, "null device pointer");
+    if (!rows || !width) return fail(ctx, B200ZK_ERR_SHAPE, "empty matrix");
+    b200zk_mat* m = new (std::nothrow) b200zk_mat();
+    if (!m) return B200ZK_ERR_OOM;
+    m->d = d;
+    m->rows = rows;
+    m->width = width;
+    m->owned = false;
+    *out = m;
+    return B200ZK_OK;
+}
+int b200zk_mat_download_rows(b200zk_ctx* ctx, const b200zk_mat* m, uint64_t row0, uint64_t nrows, uint32_t* h) {
+    TRY(check_mat(ctx, m));
+    if (!h || row0 + nrows > m->rows) return fail(ctx, B200ZK_ERR_ARG, "bad row range");
+    CU(cudaMemcpyAsync(h, m->d + row0 * m->width, nrows * m->width * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+int b200zk_mat_download(b200zk_ctx* ctx, const b200zk_mat* m, uint32_t* h) {
+    TRY(check_mat(ctx, m));
+    return b200zk_mat_download_rows(ctx, m, 0, m->rows, h);
+}
+uint64_t b200zk_mat_rows(const b200zk_mat* m) { return m ? m->rows : 0; }
+uint32_t b200zk_mat_width(const b200zk_mat* m) { return m ? m->width : 0; }
+uint32_t* b200zk_mat_device_ptr(const b200zk_mat* m) { return m ? m->d : nullptr; }
+void b200zk_mat_free(b200zk_ctx* ctx, b200zk_mat* m) {
+    if (!m) return;
+    if (m->owned && m->d) {
+        if (ctx) {
+            cudaSetDevice(ctx->device);
+            cudaStreamSynchronize(ctx->stream);
+        }
+        cudaFree(m->d);
+    }
+    delete m;
+}
+int b200zk_mat_fill(b200zk_ctx* ctx, b200zk_mat* m, uint64_t seed) {
+    TRY(check_mat(ctx, m));
+    fill_kernel<<<148 * 16, 256, 0, ctx->stream>>>(m->d, m->rows * m->width, seed);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+int b200zk_mat_checksum(b200zk_ctx* ctx, const b200zk_mat* m, uint64_t* h_out) {
+    TRY(check_mat(ctx, m));
+    if (!h_out) return fail(ctx, B200ZK_ERR_ARG, "null output");
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->d_small);
+    CU(cudaMemsetAsync(acc, 0, 8, ctx->stream));
+    checksum_kernel<<<148 * 16, 256, 0, ctx->stream>>>(m->d, m->rows * m->width, acc);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(h_out, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+// ================================================================================================ NTT / LDE
+int b200zk_coset_lde_batch_into(b200zk_ctx* ctx, const b200zk_mat* evals, uint32_t added_bits, uint32_t shift, int bitrev_rows, b200zk_mat* out) {
+    TRY(check_mat(ctx, evals));
+    TRY(check_mat(ctx, out));
+    const uint64_t N = evals->rows;
+    const uint32_t W = evals->width;
+    if (!is_pow2(N)) return fail(ctx, B200ZK_ERR_SHAPE, "height must be a power of two");
+    const int n = log2u(N);
+    if (n + (int)added_bits > MAX_LOG) return fail(ctx, B200ZK_ERR_SHAPE, "size exceeds the two-adicity of BabyBear (2^27)");
+    if (out->rows != (N << added_bits) || out->width != W) return fail(ctx, B200ZK_ERR_SHAPE, "output matrix has the wrong shape");
+    if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
+    if (out->d == evals->d) return fail(ctx, B200ZK_ERR_ARG, "output aliases input");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t C = 1u << added_bits;
+    if (n == 0) {  // constant polynomial: every evaluation equals the single input row
+        uint64_t tot = (uint64_t)C * W;
+        replicate_row_kernel<<<(uint32_t)((tot + 255) / 256), 256, 0, ctx->stream>>>(evals->d, out->d, C, W);
+        LAUNCHED();
+        return B200ZK_OK;
+    }
+    uint32_t* final_dst = out->d;
+    b200zk_mat* tmp_nat = nullptr;
+    if (!bitrev_rows) {  // natural order requested: build bit-reversed in a temporary, permute at the end
+        TRY(b200zk_mat_alloc(ctx, out->rows, W, &tmp_nat));
+        final_dst = tmp_nat->d;
+    }
+    // coefficients (natural order, unscaled by 1/N) land in the last N-row block of the output;
+    // with added_bits == 0 that block is the whole output, so the inverse transform needs its own work area
+    uint32_t* coef = final_dst + (uint64_t)(C - 1) * N * W;
+    b200zk_mat* tmp_inv = nullptr;
+    uint32_t* inv_work = final_dst;  // block 0
+    if (C == 1) {
+        TRY(b200zk_mat_alloc(ctx, N, W, &tmp_inv));
+        inv_work = tmp_inv->d;
+    }
+    int rc = run_transform(ctx, evals->d, inv_work, coef, n, W, /*inverse=*/1, Scale{}, Scale{}, /*out_natural=*/1);
+    // per-coset scale tables: (shift * w'^bitrev(c))^j / N
+    const size_t per = lo_words(N) + hi_words(N);
+    if (rc == B200ZK_OK) rc = ensure_tab(ctx, per * C);
+    const uint32_t wprime = bb::two_adic_generator(n + (int)added_bits);
+    const uint32_t ninv = bb::inv(bb::to_monty((uint32_t)(N % bb::P)));
+    for (uint32_t c = 0; c < C && rc == B200ZK_OK; c++) {
+        uint32_t base = bb::mul(shift, bb::pow(wprime, bb::bitrev(c, (int)added_bits)));
+        rc = pow_tables(ctx, ctx->tab + per * c, ctx->tab + per * c + lo_words(N), base, ninv, N);
+    }
+    for (uint32_t c = 0; c < C && rc == B200ZK_OK; c++) {  // the block holding the coefficients goes last (in place)
+        uint32_t* dst = final_dst + (uint64_t)c * N * W;
+        Scale pre{ctx->tab + per * c, ctx->tab + per * c + lo_words(N)};
+        rc = run_transform(ctx, coef, dst, dst, n, W, /*inverse=*/0, pre, Scale{}, 0);
+    }
+    if (rc == B200ZK_OK && !bitrev_rows) {
+        const int nb = n + (int)added_bits;
+        const int vec = (W % 4 == 0) ? 4 : 1;
+        uint64_t threads = out->rows * ((W + vec - 1) / vec);
+        if (vec == 4) ntt::bitrev_rows_kernel<4><<<(uint32_t)((threads + 255) / 256), 256, 0, ctx->stream>>>(final_dst, out->d, nb, W);
+        else ntt::bitrev_rows_kernel<1><<<(uint32_t)((threads + 255) / 256), 256, 0, ctx->stream>>>(final_dst, out->d, nb, W);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "bitrev_rows launch failed");
+    }
+    if (tmp_inv) b200zk_mat_free(ctx, tmp_inv);
+    if (tmp_nat) b200zk_mat_free(ctx, tmp_nat);
+    return rc;
+}
+
+int b200zk_coset_lde_batch(b200zk_ctx* ctx, const b200zk_mat* evals, uint32_t added_bits, uint32_t shift, int bitrev_rows, b200zk_mat** out) {
+    if (!out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    TRY(check_mat(ctx, evals));
+    if (added_bits > MAX_LOG) return fail(ctx, B200ZK_ERR_SHAPE, "added_bits too large");
+    TRY(b200zk_mat_alloc(ctx, evals->rows << added_bits, evals->width, out));
+    int rc = b200zk_coset_lde_batch_into(ctx, evals, added_bits, shift, bitrev_rows, *out);
+    if (rc) {
+        b200zk_mat_free(ctx, *out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int b200zk_dft_batch(b200zk_ctx* ctx, const b200zk_mat* in, uint32_t shift, int inverse, int bitrev_rows, b200zk_mat** out) {
+    if (!out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    TRY(check_mat(ctx, in));
+    const uint64_t N = in->rows;
+    const uint32_t W = in->width;
+    if (!is_pow2(N)) return fail(ctx, B200ZK_ERR_SHAPE, "height must be a power of two");
+    const int n = log2u(N);
+    if (n > MAX_LOG) return fail(ctx, B200ZK_ERR_SHAPE, "size exceeds the two-adicity of BabyBear (2^27)");
+    if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
+    CU(cudaSetDevice(ctx->device));
+    TRY(b200zk_mat_alloc(ctx, N, W, out));
+    int rc = B200ZK_OK;
+    if (n == 0) {
+        CU(cudaMemcpyAsync((*out)->d, in->d, (size_t)W * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return rc;
+    }
+    Scale pre, post;
+    const size_t per = lo_words(N) + hi_words(N);
+    rc = ensure_tab(ctx, per);
+    if (rc == B200ZK_OK && !inverse && shift != bb::ONE) {
+        rc = pow_tables(ctx, ctx->tab, ctx->tab + lo_words(N), shift, bb::ONE, N);
+        pre = Scale{ctx->tab, ctx->tab + lo_words(N)};
+    }
+    if (rc == B200ZK_OK && inverse) {
+        rc = pow_tables(ctx, ctx->tab, ctx->tab + lo_words(N), bb::inv(shift), bb::inv(bb::to_monty((uint32_t)(N % bb::P))), N);
+        post = Scale{ctx->tab, ctx->tab + lo_words(N)};
+    }
+    const bool natural = !bitrev_rows;
+    const bool multi = make_plan(n).size() > 1;
+    b200zk_mat* tmp = nullptr;
+    uint32_t* work = (*out)->d;
+    if (rc == B200ZK_OK && natural && multi) {  // the scattering last pass must not run in place
+        rc = b200zk_mat_alloc(ctx, N, W, &tmp);
+        if (rc == B200ZK_OK) work = tmp->d;
+    }
+    if (rc == B200ZK_OK) rc = run_transform(ctx, in->d, work, (*out)->d, n, W, inverse, pre, post, natural ? 1 : 0);
+    if (tmp) b200zk_mat_free(ctx, tmp);
+    if (rc) {
+        b200zk_mat_free(ctx, *out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+// ================================================================================================ Poseidon2
+int b200zk_poseidon2_permute_dev(b200zk_ctx* ctx, uint32_t* d_states, uint64_t n) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_states) return fail(ctx, B200ZK_ERR_ARG, "null states");
+    if (!n) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    mk::permute_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(d_states, n, 0);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+// same permutation through the straightforward formulation (cross-check of the optimised kernel)
+int b200zk_poseidon2_permute_plain_dev(b200zk_ctx* ctx, uint32_t* d_states, uint64_t n) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_states) return fail(ctx, B200ZK_ERR_ARG, "null states");
+    if (!n) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    mk::permute_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(d_states, n, 1);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+int b200zk_poseidon2_permute(b200zk_ctx* ctx, uint32_t* h_states, uint64_t n) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!h_states) return fail(ctx, B200ZK_ERR_ARG, "null states");
+    if (!n) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d = nullptr;
+    TRY(dev_alloc(ctx, n * 64, (void**)&d));
+    int rc = B200ZK_OK;
+    cudaError_t e = cudaMemcpyAsync(d, h_states, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = b200zk_poseidon2_permute_dev(ctx, d, n);
+    if (e == cudaSuccess && rc == B200ZK_OK) e = cudaMemcpyAsync(h_states, d, n * 64, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+static int make_group(b200zk_ctx* ctx, b200zk_mat* const* mats, const uint32_t* idx, uint32_t cnt, mk::Group* g) {
+    if (cnt > (uint32_t)mk::MAX_GROUP) return fail(ctx, B200ZK_ERR_SHAPE, "more than 128 matrices of one height in a commit");
+    g->n = (int)cnt;
+    g->fast8 = cnt > 0;
+    for (uint32_t i = 0; i < cnt; i++) {
+        const b200zk_mat* m = mats[idx[i]];
+        g->m[i].ptr = m->d;
+        g->m[i].width = m->width;
+        if (m->width % 8 != 0 || ((uintptr_t)m->d % 32) != 0) g->fast8 = 0;
+    }
+    return B200ZK_OK;
+}
+
+int b200zk_hash_rows_dev(b200zk_ctx* ctx, const b200zk_mat* m, uint32_t* d_digests) {
+    TRY(check_mat(ctx, m));
+    if (!d_digests) return fail(ctx, B200ZK_ERR_ARG, "null digests");
+    CU(cudaSetDevice(ctx->device));
+    mk::Group g;
+    b200zk_mat* one[1] = {const_cast<b200zk_mat*>(m)};
+    uint32_t idx0 = 0;
+    TRY(make_group(ctx, one, &idx0, 1, &g));
+    mk::leaf_hash_kernel<<<(uint32_t)((m->rows + 255) / 256), 256, 0, ctx->stream>>>(g, m->rows, d_digests);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+int b200zk_hash_rows(b200zk_ctx* ctx, const b200zk_mat* m, uint32_t* h_digests) {
+    TRY(check_mat(ctx, m));
+    if (!h_digests) return fail(ctx, B200ZK_ERR_ARG, "null digests");
+    uint32_t* d = nullptr;
+    TRY(dev_alloc(ctx, m->rows * 32, (void**)&d));
+    int rc = b200zk_hash_rows_dev(ctx, m, d);
+    cudaError_t e = cudaSuccess;
+    if (rc == B200ZK_OK) e = cudaMemcpyAsync(h_digests, d, m->rows * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+int b200zk_compress_pairs_dev(b200zk_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_in || !d_out) return fail(ctx, B200ZK_ERR_ARG, "null buffer");
+    if (!n) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    mk::Group g;
+    g.n = 0;
+    g.fast8 = 0;
+    mk::compress_layer_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_out, n, g);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+int b200zk_compress_pairs(b200zk_ctx* ctx, const uint32_t* h_in, uint32_t* h_out, uint64_t n) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!h_in || !h_out) return fail(ctx, B200ZK_ERR_ARG, "null buffer");
+    if (!n) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d = nullptr;
+    TRY(dev_alloc(ctx, n * 96, (void**)&d));
+    cudaError_t e = cudaMemcpyAsync(d, h_in, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = B200ZK_OK;
+    if (e == cudaSuccess) rc = b200zk_compress_pairs_dev(ctx, d, d + 16 * n, n);
+    if (e == cudaSuccess && rc == B200ZK_OK) e = cudaMemcpyAsync(h_out, d + 16 * n, n * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+// ================================================================================================ Merkle
+void b200zk_tree_free(b200zk_ctx* ctx, b200zk_tree* t) {
+    if (!t) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(t->d_digests);
+    cudaFree(t->d_open);
+    if (t->owns_mats)
+        for (auto* m : t->mats) b200zk_mat_free(ctx, m);
+    delete t;
+}
+
+// builds the tree on the stream; the root stays on the device (last digest); no synchronisation
+static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, int take, b200zk_tree** out) {
+    *out = nullptr;
+    if (!k || !mats) return fail(ctx, B200ZK_ERR_ARG, "no matrices");
+    for (uint32_t i = 0; i < k; i++) {
+        TRY(check_mat(ctx, mats[i]));
+        if (!is_pow2(mats[i]->rows)) return fail(ctx, B200ZK_ERR_SHAPE, "matrix heights must be powers of two");
+    }
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> order(k);
+    for (uint32_t i = 0; i < k; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return mats[a]->rows > mats[b]->rows; });
+    b200zk_tree* t = new (std::nothrow) b200zk_tree();
+    if (!t) return B200ZK_ERR_OOM;
+    t->max_h = mats[order[0]]->rows;
+    t->depth = (uint32_t)log2u(t->max_h);
+    t->mats.assign(mats, mats + k);
+    t->owns_mats = false;  // set at the very end so a failed commit never frees the caller's matrices
+    int rc = dev_alloc(ctx, (2 * t->max_h - 1) * 32, (void**)&t->d_digests);
+    if (rc == B200ZK_OK) rc = dev_alloc(ctx, sizeof(mk::OpenMat) * k, (void**)&t->d_open);
+    if (rc == B200ZK_OK) {
+        std::vector<mk::OpenMat> om(k);
+        uint64_t off = 0;
+        for (uint32_t i = 0; i < k; i++) {
+            om[i].ptr = mats[i]->d;
+            om[i].width = mats[i]->width;
+            om[i].shift = t->depth - (uint32_t)log2u(mats[i]->rows);
+            om[i].out_off = off;
+            off += mats[i]->width;
+        }
+        t->total_width = off;
+        cudaError_t e = cudaMemcpyAsync(t->d_open, om.data(), sizeof(mk::OpenMat) * k, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // om is a stack/heap temporary
+        if (e != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    }
+    uint64_t off = 0;
+    for (uint64_t n = t->max_h; n >= 1; n >>= 1) {
+        t->layer_off.push_back(off);
+        off += n;
+        if (n == 1) break;
+    }
+    uint32_t pos = 0;
+    if (rc == B200ZK_OK) {
+        uint32_t g0 = pos;
+        while (pos < k && mats[order[pos]]->rows == t->max_h) pos++;
+        mk::Group g;
+        rc = make_group(ctx, mats, order.data() + g0, pos - g0, &g);
+        if (rc == B200ZK_OK) {
+            mk::leaf_hash_kernel<<<(uint32_t)((t->max_h + 255) / 256), 256, 0, ctx->stream>>>(g, t->max_h, t->d_digests);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "leaf_hash launch failed");
+        }
+    }
+    uint32_t layer = 0;
+    for (uint64_t len = t->max_h; len > 1 && rc == B200ZK_OK; len >>= 1, layer++) {
+        const uint64_t n_next = len >> 1;
+        uint32_t* prev = t->d_digests + 8 * t->layer_off[layer];
+        uint32_t* next = t->d_digests + 8 * t->layer_off[layer + 1];
+        if (pos == k && len <= TOP_LAYER) {  // nothing left to inject: one CTA finishes the tree
+            mk::compress_top_kernel<<<1, 1024, 0, ctx->stream>>>(prev, (uint32_t)len);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "compress_top launch failed");
+            break;
+        }
+        uint32_t g0 = pos;
+        while (pos < k && mats[order[pos]]->rows == n_next) pos++;
+        mk::Group g;
+        rc = make_group(ctx, mats, order.data() + g0, pos - g0, &g);
+        if (rc != B200ZK_OK) break;
+        mk::compress_layer_kernel<<<(uint32_t)((n_next + 255) / 256), 256, 0, ctx->stream>>>(prev, next, n_next, g);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "compress_layer launch failed");
+    }
+    if (rc == B200ZK_OK && pos != k) rc = fail(ctx, B200ZK_ERR_SHAPE, "matrix height not reached while building the tree");
+    if (rc != B200ZK_OK) {
+        b200zk_tree_free(ctx, t);
+        return rc;
+    }
+    t->owns_mats = take != 0;
+    *out = t;
+    return B200ZK_OK;
+}
+
+int b200zk_tree_root(b200zk_ctx* ctx, const b200zk_tree* t, uint32_t h_root[8]) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!t || !h_root) return fail(ctx, B200ZK_ERR_ARG, "null tree/root");
+    CU(cudaMemcpyAsync(h_root, t->d_digests + 8 * (2 * t->max_h - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_merkle_commit(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, int take, uint32_t h_root[8], b200zk_tree** out) {
+    if (!ctx || !out) return B200ZK_ERR_ARG;
+    TRY(commit_async(ctx, mats, k, take, out));
+    if (h_root) {
+        int rc = b200zk_tree_root(ctx, *out, h_root);
+        if (rc) {
+            (*out)->owns_mats = false;
+            b200zk_tree_free(ctx, *out);
+            *out = nullptr;
+            return rc;
+        }
+    }
+    return B200ZK_OK;
+}
+
+int b200zk_lde_commit(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uint32_t added_bits, const uint32_t* shifts, uint32_t h_root[8],
+                      b200zk_tree** out) {
+    if (!ctx || !out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    if (!k || !evals || !shifts) return fail(ctx, B200ZK_ERR_ARG, "no matrices");
+    std::vector<b200zk_mat*> ldes(k, nullptr);
+    int rc = B200ZK_OK;
+    for (uint32_t i = 0; i < k && rc == B200ZK_OK; i++) rc = b200zk_coset_lde_batch(ctx, evals[i], added_bits, shifts[i], 1, &ldes[i]);
+    if (rc == B200ZK_OK) rc = b200zk_merkle_commit(ctx, ldes.data(), k, /*take=*/1, h_root, out);
+    if (rc != B200ZK_OK)
+        for (auto* m : ldes) b200zk_mat_free(ctx, m);
+    return rc;
+}
+
+uint32_t b200zk_tree_depth(const b200zk_tree* t) { return t ? t->depth : 0; }
+uint32_t b200zk_tree_num_mats(const b200zk_tree* t) { return t ? (uint32_t)t->mats.size() : 0; }
+uint64_t b200zk_tree_total_width(const b200zk_tree* t) { return t ? t->total_width : 0; }
+const b200zk_mat* b200zk_tree_mat(const b200zk_tree* t, uint32_t i) { return (t && i < t->mats.size()) ? t->mats[i] : nullptr; }
+int b200zk_tree_download_layer(b200zk_ctx* ctx, const b200zk_tree* t, uint32_t layer, uint32_t* h) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!t || !h || layer > t->depth) return fail(ctx, B200ZK_ERR_ARG, "bad layer");
+    CU(cudaMemcpyAsync(h, t->d_digests + 8 * t->layer_off[layer], (t->max_h >> layer) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_merkle_open(b200zk_ctx* ctx, const b200zk_tree* t, uint64_t index, uint32_t* h_rows, uint32_t* h_path) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!t || !h_rows || (!h_path && t->depth)) return fail(ctx, B200ZK_ERR_ARG, "null tree/output");
+    if (index >= t->max_h) return fail(ctx, B200ZK_ERR_ARG, "index out of range");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d = nullptr;
+    const size_t words = t->total_width + 8ull * t->depth;
+    TRY(dev_alloc(ctx, words * 4, (void**)&d));
+    const uint32_t k = (uint32_t)t->mats.size();
+    mk::open_rows_kernel<<<std::min<uint32_t>(k, 1024), 128, 0, ctx->stream>>>(t->d_open, k, index, d);
+    ctx->launches++;
+    if (t->depth) {
+        mk::open_path_kernel<<<t->depth, 32, 0, ctx->stream>>>(t->d_digests, t->max_h, t->depth, index, d + t->total_width);
+        ctx->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_rows, d, t->total_width * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && t->depth) e = cudaMemcpyAsync(h_path, d + t->total_width, 32ull * t->depth, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    return B200ZK_OK;
+}
+
+int b200zk_merkle_verify(b200zk_ctx* ctx, const uint32_t* h_rows, const uint64_t* heights, const uint32_t* widths, uint32_t k, const uint32_t* h_path,
+                         uint32_t depth, uint64_t index, const uint32_t h_root[8], int* h_ok) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!h_rows || !heights || !widths || !k || !h_root || !h_ok || (depth && !h_path)) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    *h_ok = 0;
+    std::vector<uint32_t> order(k);
+    std::vector<uint64_t> offs(k);
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < k; i++) {
+        if (!is_pow2(heights[i])) return fail(ctx, B200ZK_ERR_SHAPE, "matrix heights must be powers of two");
+        order[i] = i;
+        offs[i] = tot;
+        tot += widths[i];
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return heights[a] > heights[b]; });
+    if ((uint32_t)log2u(heights[order[0]]) != depth) return fail(ctx, B200ZK_ERR_SHAPE, "path length does not match the tallest matrix");
+    // pack: rows (sorted order) | widths | log_heights | path | root | ok
+    std::vector<uint32_t> pack;
+    pack.reserve(tot + 2 * k + 8 * depth + 16);
+    for (uint32_t i = 0; i < k; i++) pack.insert(pack.end(), h_rows + offs[order[i]], h_rows + offs[order[i]] + widths[order[i]]);
+    const size_t o_w = pack.size();
+    for (uint32_t i = 0; i < k; i++) pack.push_back(widths[order[i]]);
+    const size_t o_h = pack.size();
+    for (uint32_t i = 0; i < k; i++) pack.push_back((uint32_t)log2u(heights[order[i]]));
+    const size_t o_p = pack.size();
+    pack.insert(pack.end(), h_path, h_path + 8 * (size_t)depth);
+    const size_t o_r = pack.size();
+    pack.insert(pack.end(), h_root, h_root + 8);
+    const size_t o_ok = pack.size();
+    pack.push_back(0);
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d = nullptr;
+    TRY(dev_alloc(ctx, pack.size() * 4, (void**)&d));
+    cudaError_t e = cudaMemcpyAsync(d, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        mk::VerifyArgs a{d, d + o_w, d + o_h, k, d + o_p, depth, index, d + o_r, reinterpret_cast<int*>(d + o_ok)};
+        mk::verify_kernel<<<1, 32, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    uint32_t ok = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&ok, d + o_ok, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    *h_ok = (int)ok;
+    return B200ZK_OK;
+}
+
+// ================================================================================================ challenger
+int b200zk_chal_create(b200zk_ctx* ctx, b200zk_chal** out) {
+    if (!ctx || !out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    b200zk_chal* c = new (std::nothrow) b200zk_chal();
+    if (!c) return B200ZK_ERR_OOM;
+    int rc = dev_alloc(ctx, sizeof(fri::ChalState), (void**)&c->d);
+    if (rc) {
+        delete c;
+        return rc;
+    }
+    CU(cudaMemsetAsync(c->d, 0, sizeof(fri::ChalState), ctx->stream));
+    *out = c;
+    return B200ZK_OK;
+}
+void b200zk_chal_free(b200zk_ctx* ctx, b200zk_chal* c) {
+    if (!c) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(c->d);
+    delete c;
+}
+int b200zk_chal_observe(b200zk_ctx* ctx, b200zk_chal* c, const uint32_t* h_values, uint32_t n) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!c || (!h_values && n)) return fail(ctx, B200ZK_ERR_ARG, "null challenger/values");
+    if (!n) return B200ZK_OK;
+    if (n > 8192) return fail(ctx, B200ZK_ERR_ARG, "observe at most 8192 elements per call");
+    for (uint32_t i = 0; i < n; i++)
+        if (h_values[i] >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "value is not a reduced field element");
+    CU(cudaMemcpyAsync(ctx->d_small, h_values, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    fri::chal_observe_kernel<<<1, 32, 0, ctx->stream>>>(c->d, ctx->d_small, n);
+    LAUNCHED();
+    CU(cudaStreamSynchronize(ctx->stream));  // d_small is reused by the next call
+    return B200ZK_OK;
+}
+static int chal_sample_impl(b200zk_ctx* ctx, b200zk_chal* c, uint32_t* h_out, uint32_t n, uint32_t bits) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!c || !h_out) return fail(ctx, B200ZK_ERR_ARG, "null challenger/output");
+    if (n > 8192 || bits > 31) return fail(ctx, B200ZK_ERR_ARG, "bad sample request");
+    if (!n) return B200ZK_OK;
+    fri::chal_sample_kernel<<<1, 32, 0, ctx->stream>>>(c->d, ctx->d_small, n, bits);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(h_out, ctx->d_small, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+int b200zk_chal_sample(b200zk_ctx* ctx, b200zk_chal* c, uint32_t* h_out, uint32_t n) { return chal_sample_impl(ctx, c, h_out, n, 0); }
+int b200zk_chal_sample_bits(b200zk_ctx* ctx, b200zk_chal* c, uint32_t bits, uint32_t* h_out) {
+    if (bits == 0) {  // sample_bits(0) still consumes a sample in p3; result is 0
+        uint32_t tmp;
+        int rc = chal_sample_impl(ctx, c, &tmp, 1, 0);
+        if (rc == B200ZK_OK && h_out) *h_out = 0;
+        return rc;
+    }
+    return chal_sample_impl(ctx, c, h_out, 1, bits);
+}
+int b200zk_chal_grind(b200zk_ctx* ctx, b200zk_chal* c, uint32_t bits, uint32_t* h_witness) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!c || !h_witness || bits > 30) return fail(ctx, B200ZK_ERR_ARG, "bad grind request");
+    uint32_t* best = ctx->d_small;
+    uint32_t init = 0xffffffffu;
+    CU(cudaMemcpyAsync(best, &init, 4, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t batch = 1u << 20;
+    uint32_t found = init;
+    for (uint64_t base = 0; base < bb::P && found == init; base += batch) {
+        uint32_t cnt = (uint32_t)std::min<uint64_t>(batch, bb::P - base);
+        fri::chal_grind_kernel<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(c->d, bits, (uint32_t)base, cnt, best);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(&found, best, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (found == init) return fail(ctx, B200ZK_ERR_ARG, "no proof-of-work witness exists");
+    fri::chal_observe_witness_kernel<<<1, 32, 0, ctx->stream>>>(c->d, best, bits);
+    LAUNCHED();
+    CU(cudaStreamSynchronize(ctx->stream));
+    *h_witness = found;
+    return B200ZK_OK;
+}
+int b200zk_chal_state(b200zk_ctx* ctx, const b200zk_chal* c, uint32_t h_state[34]) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!c || !h_state) return fail(ctx, B200ZK_ERR_ARG, "null challenger/output");
+    CU(cudaMemcpyAsync(h_state, c->d, sizeof(fri::ChalState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+// ================================================================================================ FRI
+static int fold_launch(b200zk_ctx* ctx, const uint32_t* d_in, uint64_t len, const uint32_t* d_beta, const uint32_t* d_add, int add_mode, uint32_t* tab,
+                       uint32_t* d_out) {
+    const uint64_t half = len / 2;
+    const int lh = log2u(half);
+    // powers of g^-1 (g generates the size-len subgroup) scaled by 1/2
+    const uint32_t ginv = bb::inv(bb::two_adic_generator(lh + 1));
+    TRY(pow_tables(ctx, tab, tab + 4096, ginv, bb::HALF, std::max<uint64_t>(half, 1)));
+    fri::fold_kernel<<<(uint32_t)((half + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(d_in), half, lh, d_beta, tab, tab + 4096,
+                                                                              reinterpret_cast<const uint4*>(d_add), d_add ? add_mode : 0,
+                                                                              reinterpret_cast<uint4*>(d_out));
+    LAUNCHED();
+    return B200ZK_OK;
+}
+
+int b200zk_fri_commit_layer(b200zk_ctx* ctx, const uint32_t* d_folded, uint64_t len, uint32_t h_root[8], b200zk_tree** out) {
+    if (!ctx || !out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    if (!d_folded) return fail(ctx, B200ZK_ERR_ARG, "null input");
+    if (!is_pow2(len) || len < 2) return fail(ctx, B200ZK_ERR_SHAPE, "length must be a power of two >= 2");
+    b200zk_mat* m = nullptr;
+    TRY(b200zk_mat_wrap(ctx, const_cast<uint32_t*>(d_folded), len / 2, 8, &m));
+    b200zk_mat* arr[1] = {m};
+    int rc = b200zk_merkle_commit(ctx, arr, 1, /*take=*/1, h_root, out);  // the handle (not the memory) belongs to the tree
+    if (rc) b200zk_mat_free(ctx, m);
+    return rc;
+}
+
+int b200zk_fri_fold_layer(b200zk_ctx* ctx, const uint32_t* d_folded, uint64_t len, const uint32_t h_beta[4], const uint32_t* d_add, uint32_t* d_out) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_folded || !h_beta || !d_out) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (!is_pow2(len) || len < 2) return fail(ctx, B200ZK_ERR_SHAPE, "length must be a power of two >= 2");
+    if ((len >> 1) > (1ull << MAX_LOG)) return fail(ctx, B200ZK_ERR_SHAPE, "length exceeds two-adicity");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t half = len / 2;
+    TRY(ensure_tab(ctx, 4096 + hi_words(half) + 8));
+    uint32_t* d_beta = ctx->tab + 4096 + hi_words(half);
+    CU(cudaMemcpyAsync(d_beta, h_beta, 16, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(fold_launch(ctx, d_folded, len, d_beta, d_add, 1, ctx->tab, d_out));
+    CU(cudaStreamSynchronize(ctx->stream));  // h_beta may be a stack temporary of the caller
+    return B200ZK_OK;
+}
+
+int b200zk_fri_commit_phase(b200zk_ctx* ctx, const uint32_t* const* d_inputs, const uint64_t* lens, uint32_t n_inputs, uint32_t log_blowup,
+                            uint32_t log_final_poly_len, b200zk_chal* chal, const uint32_t* h_betas_forced, uint32_t* h_roots, uint32_t* h_betas,
+                            uint32_t* h_final, b200zk_tree** trees, uint32_t* h_rounds) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_inputs || !lens || !n_inputs || !h_roots || !h_final || !h_rounds) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (!chal && !h_betas_forced) return fail(ctx, B200ZK_ERR_ARG, "need a challenger or forced betas");
+    for (uint32_t j = 0; j < n_inputs; j++) {
+        if (!d_inputs[j] || !is_pow2(lens[j])) return fail(ctx, B200ZK_ERR_SHAPE, "input lengths must be powers of two");
+        if (j && lens[j] >= lens[j - 1]) return fail(ctx, B200ZK_ERR_SHAPE, "input lengths must be strictly decreasing");
+    }
+    const uint64_t stop = 1ull << (log_blowup + log_final_poly_len);
+    const uint64_t len0 = lens[0];
+    if (len0 < stop || log2u(len0) > MAX_LOG + 1) return fail(ctx, B200ZK_ERR_SHAPE, "bad first input length");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t max_rounds = 0;
+    for (uint64_t l = len0; l > stop; l >>= 1) max_rounds++;
+    *h_rounds = max_rounds;
+    // scratch: per-round power tables + betas
+    size_t tab_per = 4096 + hi_words(len0 / 2);
+    TRY(ensure_tab(ctx, tab_per * std::max<uint32_t>(max_rounds, 1) + 4 * (size_t)max_rounds + 16));
+    uint32_t* d_betas = ctx->tab + tab_per * std::max<uint32_t>(max_rounds, 1);
+    if (h_betas_forced && max_rounds) CU(cudaMemcpyAsync(d_betas, h_betas_forced, 16ull * max_rounds, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<b200zk_tree*> made;
+    const uint32_t* cur = d_inputs[0];
+    uint32_t* owned_cur = nullptr;  // folded vectors we allocated (round >= 1 leaves live in their tree's matrix)
+    uint64_t len = len0;
+    uint32_t next_in = 1;
+    int rc = B200ZK_OK;
+    for (uint32_t r = 0; r < max_rounds && rc == B200ZK_OK; r++) {
+        // commit the (len/2) x 2 EF4 matrix = (len/2) x 8 base matrix
+        b200zk_mat* leaves = nullptr;
+        rc = b200zk_mat_wrap(ctx, const_cast<uint32_t*>(cur), len / 2, 8, &leaves);
+        if (rc) break;
+        if (owned_cur) leaves->owned = true;  // the tree frees the folded vector with its leaves
+        b200zk_tree* t = nullptr;
+        b200zk_mat* arr[1] = {leaves};
+        rc = commit_async(ctx, arr, 1, /*take=*/1, &t);
+        if (rc) {
+            leaves->owned = false;
+            b200zk_mat_free(ctx, leaves);
+            break;
+        }
+        owned_cur = nullptr;
+        made.push_back(t);
+        const uint32_t* d_root = t->d_digests + 8 * (2 * t->max_h - 2);
+        cudaError_t e = cudaMemcpyAsync(h_roots + 8 * r, d_root, 32, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e)); break; }
+        if (!h_betas_forced) {
+            fri::chal_fri_round_kernel<<<1, 32, 0, ctx->stream>>>(chal->d, d_root, d_betas + 4 * r);
+            ctx->launches++;
+        }
+        uint32_t* nxt = nullptr;
+        rc = dev_alloc(ctx, (len / 2) * 16, (void**)&nxt);
+        if (rc) break;
+        const uint32_t* add = nullptr;
+        if (next_in < n_inputs && lens[next_in] == len / 2) add = d_inputs[next_in++];
+        rc = fold_launch(ctx, cur, len, d_betas + 4 * r, add, 1, ctx->tab + tab_per * r, nxt);
+        if (rc) { cudaFree(nxt); break; }
+        cur = nxt;
+        owned_cur = nxt;
+        len >>= 1;
+    }
+    if (rc == B200ZK_OK) {
+        cudaError_t e = cudaMemcpyAsync(h_final, cur, len * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && h_betas && max_rounds) e = cudaMemcpyAsync(h_betas, d_betas, 16ull * max_rounds, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (owned_cur) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(owned_cur);
+    }
+    if (rc == B200ZK_OK && trees) {
+        for (uint32_t r = 0; r < max_rounds; r++) trees[r] = made[r];
+    } else {
+        for (auto* t : made) b200zk_tree_free(ctx, t);
+    }
+    return rc;
+}
+
+// ================================================================================================ raw memory
+int b200zk_dev_alloc(b200zk_ctx* ctx, uint64_t bytes, void** d_out) {
+    if (!ctx || !d_out) return B200ZK_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    return dev_alloc(ctx, bytes, d_out);
+}
+void b200zk_dev_free(b200zk_ctx* ctx, void* d) {
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+}
+int b200zk_dev_upload(b200zk_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_dst || !h_src) return fail(ctx, B200ZK_ERR_ARG, "null pointer");
+    CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+int b200zk_dev_download(b200zk_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!h_dst || !d_src) return fail(ctx, B200ZK_ERR_ARG, "null pointer");
+    CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+}  // extern "C"

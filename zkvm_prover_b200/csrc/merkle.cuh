@@ -1,0 +1,221 @@
+// K4/K5: PaddingFreeSponge leaf hashing and TruncatedPermutation tree compression for
+// MerkleTreeMmcs<.., 8> (p3-merkle-tree MerkleTree::new: first_digest_layer + compress_and_inject; v1-era
+// crate that produced the reference's proof fixtures, see tests/golden).  One permutation chain per
+// thread; the kernels are integer-pipe bound, loads are issued one permutation ahead.
+#pragma once
+#include "poseidon2.cuh"
+
+namespace mk {
+
+constexpr int MAX_GROUP = 128;  // matrices of one height class hashed into one sponge per launch
+
+struct MatRef {
+    const uint32_t* ptr;
+    uint32_t width;
+};
+struct Group {
+    MatRef m[MAX_GROUP];
+    int n;
+    int fast8;  // every matrix: width % 8 == 0 and 32-byte aligned base  -> vector path
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// sponge over the concatenation of row `row` of every matrix of the group -> st[0..8]
+__device__ __forceinline__ void sponge_rows(const Group& g, uint64_t row, uint32_t (&st)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) st[i] = 0;
+    if (g.fast8) {
+        for (int m = 0; m < g.n; m++) {
+            const uint32_t w = g.m[m].width;
+            const uint4* p = reinterpret_cast<const uint4*>(g.m[m].ptr + row * w);
+            const uint32_t chunks = w >> 3;
+            uint4 a = ldg_stream(p), b = ldg_stream(p + 1);
+            for (uint32_t c = 0; c < chunks; c++) {
+                st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w;
+                st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
+                if (c + 1 < chunks) {  // prefetch the next 32 bytes under the permutation
+                    a = ldg_stream(p + 2 * (c + 1));
+                    b = ldg_stream(p + 2 * (c + 1) + 1);
+                }
+                p2::permute(st);
+            }
+        }
+        return;
+    }
+    int fill = 0;
+    for (int m = 0; m < g.n; m++) {
+        const uint32_t w = g.m[m].width;
+        const uint32_t* p = g.m[m].ptr + row * w;
+        for (uint32_t c = 0; c < w; c++) {
+            uint32_t x = __ldg(p + c);
+#pragma unroll
+            for (int i = 0; i < 8; i++) st[i] = (fill == i) ? x : st[i];
+            if (++fill == 8) {
+                p2::permute(st);
+                fill = 0;
+            }
+        }
+    }
+    if (fill) p2::permute(st);
+}
+
+__device__ __forceinline__ void store_digest(uint32_t* out, const uint32_t (&st)[16]) {
+    uint4* o = reinterpret_cast<uint4*>(out);
+    o[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    o[1] = make_uint4(st[4], st[5], st[6], st[7]);
+}
+
+// first_digest_layer: digests[i] = hash_iter(concat rows i of the tallest matrices)
+__global__ void __launch_bounds__(256) leaf_hash_kernel(const __grid_constant__ Group g, uint64_t rows, uint32_t* __restrict__ digests) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    uint32_t st[16];
+    sponge_rows(g, i, st);
+    store_digest(digests + 8 * i, st);
+}
+
+__device__ __forceinline__ void compress_node(const uint32_t* __restrict__ prev, uint64_t i, uint32_t (&st)[16]) {
+    const uint4* p = reinterpret_cast<const uint4*>(prev + 16 * i);
+    uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+    st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w; st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
+    st[8] = c.x; st[9] = c.y; st[10] = c.z; st[11] = c.w; st[12] = d.x; st[13] = d.y; st[14] = d.z; st[15] = d.w;
+    p2::permute(st);
+}
+
+// compress_and_inject: next[i] = compress(prev[2i], prev[2i+1]); if matrices of this height exist:
+// next[i] = compress(next[i], hash_iter(rows i of those))
+__global__ void __launch_bounds__(256) compress_layer_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, uint64_t n_next,
+                                                             const __grid_constant__ Group g) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_next) return;
+    uint32_t st[16];
+    compress_node(prev, i, st);
+    if (g.n > 0) {
+        uint32_t h[16];
+        sponge_rows(g, i, h);
+#pragma unroll
+        for (int k = 0; k < 8; k++) st[8 + k] = h[k];
+        p2::permute(st);
+    }
+    store_digest(next + 8 * i, st);
+}
+
+// the top of the tree (no injected matrices): layers n0 -> n0/2 -> ... -> 1 in one CTA
+__global__ void __launch_bounds__(1024) compress_top_kernel(uint32_t* __restrict__ layers /* layer of n0 digests, followed by the next ones */, uint32_t n0) {
+    uint32_t* prev = layers;
+    for (uint32_t n = n0 >> 1; n >= 1; n >>= 1) {
+        uint32_t* next = prev + 16ull * n;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t st[16];
+            compress_node(prev, i, st);
+            store_digest(next + 8 * i, st);
+        }
+        __syncthreads();
+        prev = next;
+        if (n == 1) break;
+    }
+}
+
+// standalone K3/K5 entry points
+__global__ void __launch_bounds__(256) permute_kernel(uint32_t* __restrict__ states, uint64_t n, int plain) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4* p = reinterpret_cast<uint4*>(states + 16 * i);
+    uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+    uint32_t st[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    if (plain) p2::permute_plain(st); else p2::permute(st);
+    p[0] = make_uint4(st[0], st[1], st[2], st[3]);
+    p[1] = make_uint4(st[4], st[5], st[6], st[7]);
+    p[2] = make_uint4(st[8], st[9], st[10], st[11]);
+    p[3] = make_uint4(st[12], st[13], st[14], st[15]);
+}
+
+// Mmcs::open_batch gather: rows of every matrix at index >> shift, and the sibling path
+struct OpenMat {
+    const uint32_t* ptr;
+    uint32_t width;
+    uint32_t shift;      // log2(max_height) - log2(height)
+    uint64_t out_off;    // offset in rows_out
+};
+__global__ void open_rows_kernel(const OpenMat* __restrict__ mats, uint32_t nmats, uint64_t index, uint32_t* __restrict__ rows_out) {
+    for (uint32_t m = blockIdx.x; m < nmats; m += gridDim.x) {
+        OpenMat om = mats[m];
+        const uint32_t* src = om.ptr + (index >> om.shift) * om.width;
+        for (uint32_t c = threadIdx.x; c < om.width; c += blockDim.x) rows_out[om.out_off + c] = src[c];
+    }
+}
+__global__ void open_path_kernel(const uint32_t* __restrict__ digests, uint64_t max_h, uint32_t depth, uint64_t index, uint32_t* __restrict__ path_out) {
+    // digests: layer 0 (max_h) | layer 1 (max_h/2) | ...
+    uint32_t d = blockIdx.x;
+    if (d >= depth) return;
+    uint64_t off = 0, n = max_h;
+    for (uint32_t k = 0; k < d; k++) { off += n; n >>= 1; }
+    uint64_t sib = (index >> d) ^ 1;
+    if (threadIdx.x < 8) path_out[8 * d + threadIdx.x] = digests[8 * (off + sib) + threadIdx.x];
+}
+
+// MerkleTreeMmcs::verify_batch, single thread (tiny; device so the host mirror has no CPU hash)
+struct VerifyArgs {
+    const uint32_t* rows;       // concatenated opened rows, sorted order (tallest first)
+    const uint32_t* widths;     // per matrix, sorted order
+    const uint32_t* log_heights;
+    uint32_t k;
+    const uint32_t* path;
+    uint32_t depth;
+    uint64_t index;
+    const uint32_t* root;
+    int* ok;
+};
+__global__ void verify_kernel(VerifyArgs a) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t pos = 0;
+    uint64_t off = 0;
+    uint32_t node[16], h[16];
+    auto absorb_group = [&](uint32_t lh, uint32_t (&st)[16]) -> bool {
+        for (int i = 0; i < 16; i++) st[i] = 0;
+        int fill = 0;
+        bool any = false;
+        while (pos < a.k && a.log_heights[pos] == lh) {
+            any = true;
+            for (uint32_t c = 0; c < a.widths[pos]; c++) {
+                uint32_t x = a.rows[off + c];
+#pragma unroll
+                for (int i = 0; i < 8; i++) st[i] = (fill == i) ? x : st[i];
+                if (++fill == 8) { p2::permute(st); fill = 0; }
+            }
+            off += a.widths[pos];
+            pos++;
+        }
+        if (fill) p2::permute(st);
+        return any;
+    };
+    uint32_t lh = a.log_heights[0];
+    absorb_group(lh, node);
+    uint64_t index = a.index;
+    for (uint32_t d = 0; d < a.depth; d++) {
+        uint32_t st[16];
+        const uint32_t* sib = a.path + 8 * d;
+        if (index & 1) { for (int i = 0; i < 8; i++) { st[i] = sib[i]; st[8 + i] = node[i]; } }
+        else { for (int i = 0; i < 8; i++) { st[i] = node[i]; st[8 + i] = sib[i]; } }
+        p2::permute(st);
+        for (int i = 0; i < 8; i++) node[i] = st[i];
+        index >>= 1;
+        lh--;
+        if (pos < a.k && a.log_heights[pos] == lh) {
+            absorb_group(lh, h);
+            for (int i = 0; i < 8; i++) st[i] = node[i], st[8 + i] = h[i];
+            p2::permute(st);
+            for (int i = 0; i < 8; i++) node[i] = st[i];
+        }
+    }
+    int ok = (pos == a.k) && (lh == 0);
+    for (int i = 0; i < 8; i++) ok &= (node[i] == a.root[i]);
+    *a.ok = ok;
+}
+
+}  // namespace mk

@@ -1,0 +1,141 @@
+"""Host mirror of the FRI pieces on the path (v1-era p3-fri): TwoAdicFriPcs::commit (coset LDE of every
+trace + one MMCS commit), prover::commit_phase and TwoAdicFriGenericConfig::fold_matrix."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from .challenger import DuplexChallenger
+from .device import Context, DeviceMatrix, default_context
+from .field import GENERATOR_MONTY, P, monty_scalar
+from .mmcs import DIGEST, MerkleTreeMmcs, ProverData
+
+
+@dataclass
+class FriConfig:
+    """p3_fri::FriConfig fields that matter for the commit phase (reference values:
+    crates/circuits/chunk-circuit/openvm.toml:1-6 -> log_blowup = 1, num_queries = 100, pow bits 16)."""
+    log_blowup: int = 1
+    log_final_poly_len: int = 0
+    num_queries: int = 100
+    proof_of_work_bits: int = 16
+
+    def blowup(self) -> int:
+        return 1 << self.log_blowup
+
+    def final_poly_len(self) -> int:
+        return 1 << self.log_final_poly_len
+
+
+def fold_matrix(beta, folded, ctx: Context | None = None, add=None) -> np.ndarray:
+    """fold_matrix(beta, (len/2) x 2 EF4 matrix) -> len/2 EF4.  `folded`: (len, 4) uint32, bit-reversed order."""
+    ctx = ctx or default_context()
+    v = np.ascontiguousarray(folded, dtype=np.uint32).reshape(-1, 4)
+    n = v.shape[0]
+    d_in, d_out, d_add = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ctx.check(ctx.lib.b200zk_dev_alloc(ctx.h, n * 16, C.byref(d_in)))
+    ctx.check(ctx.lib.b200zk_dev_alloc(ctx.h, max(n // 2, 1) * 16, C.byref(d_out)))
+    try:
+        ctx.check(ctx.lib.b200zk_dev_upload(ctx.h, d_in, v.ctypes.data, n * 16))
+        if add is not None:
+            a = np.ascontiguousarray(add, dtype=np.uint32).reshape(-1, 4)
+            ctx.check(ctx.lib.b200zk_dev_alloc(ctx.h, a.nbytes, C.byref(d_add)))
+            ctx.check(ctx.lib.b200zk_dev_upload(ctx.h, d_add, a.ctypes.data, a.nbytes))
+        b = np.ascontiguousarray(beta, dtype=np.uint32)
+        ctx.check(ctx.lib.b200zk_fri_fold_layer(ctx.h, d_in, n, b.ctypes.data, d_add if add is not None else None, d_out))
+        out = np.empty((n // 2, 4), np.uint32)
+        ctx.check(ctx.lib.b200zk_dev_download(ctx.h, out.ctypes.data, d_out, out.nbytes))
+        return out
+    finally:
+        for d in (d_in, d_out, d_add):
+            if d:
+                ctx.lib.b200zk_dev_free(ctx.h, d)
+
+
+@dataclass
+class CommitPhaseResult:
+    commits: np.ndarray      # rounds x 8
+    data: list               # ProverData per round
+    final_poly: np.ndarray   # last folded vector, bit-reversed order (blowup * final_poly_len EF4)
+    betas: np.ndarray        # rounds x 4
+
+
+def commit_phase(config: FriConfig, inputs, challenger: DuplexChallenger | None, ctx: Context | None = None, betas=None,
+                 keep_trees: bool = True) -> CommitPhaseResult:
+    """p3_fri::prover::commit_phase.  inputs: list of (len_j, 4) EF4 vectors (bit-reversed order, strictly
+    decreasing power-of-two lengths) as host arrays or (device_ptr, len) pairs.  The whole loop (commit,
+    observe, sample beta, fold, roll-in) runs on the device; `betas` forces the challenges (tests)."""
+    ctx = ctx or default_context()
+    lib = ctx.lib
+    ptrs, lens, owned = [], [], []
+    try:
+        for v in inputs:
+            if isinstance(v, tuple):
+                ptrs.append(v[0])
+                lens.append(v[1])
+                continue
+            a = np.ascontiguousarray(v, dtype=np.uint32).reshape(-1, 4)
+            d = C.c_void_p()
+            ctx.check(lib.b200zk_dev_alloc(ctx.h, a.nbytes, C.byref(d)))
+            owned.append(d)
+            ctx.check(lib.b200zk_dev_upload(ctx.h, d, a.ctypes.data, a.nbytes))
+            ptrs.append(d.value)
+            lens.append(a.shape[0])
+        stop = 1 << (config.log_blowup + config.log_final_poly_len)
+        max_rounds = max(int(lens[0]).bit_length(), 1)
+        roots = np.zeros((max_rounds, DIGEST), np.uint32)
+        bout = np.zeros((max_rounds, 4), np.uint32)
+        final = np.zeros((stop, 4), np.uint32)
+        trees = (C.c_void_p * max_rounds)()
+        rounds = C.c_uint32()
+        bf = None
+        if betas is not None:
+            bf = np.ascontiguousarray(betas, dtype=np.uint32)
+        ctx.check(lib.b200zk_fri_commit_phase(
+            ctx.h, (C.c_void_p * len(ptrs))(*ptrs), (C.c_uint64 * len(lens))(*lens), len(ptrs), config.log_blowup,
+            config.log_final_poly_len, challenger.h if challenger is not None else None, bf.ctypes.data if bf is not None else None,
+            roots.ctypes.data, bout.ctypes.data, final.ctypes.data, trees if keep_trees else None, C.byref(rounds)))
+        r = rounds.value
+        data = [ProverData(ctx, C.c_void_p(trees[i]), []) for i in range(r)] if keep_trees else []
+        res = CommitPhaseResult(roots[:r].copy(), data, final, bout[:r].copy())
+        res._input_buffers = owned  # round-0 leaves alias the first input: keep it alive with the result
+        owned = []
+        return res
+    finally:
+        for d in owned:
+            lib.b200zk_dev_free(ctx.h, d)
+
+
+class TwoAdicFriPcs:
+    """The commit half of p3_fri::TwoAdicFriPcs: `commit(evaluations)` = coset LDE of every trace matrix with
+    shift GENERATOR / domain_shift (= 31 for the shift-1 trace domains OpenVM uses), rows kept in
+    bit-reversed order, then one MerkleTreeMmcs commit over all LDEs.  The LDEs never leave the device."""
+
+    def __init__(self, config: FriConfig | None = None, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.config = config or FriConfig()
+        self.mmcs = MerkleTreeMmcs(self.ctx)
+
+    def commit(self, evaluations, domain_shifts=None):
+        """evaluations: list of trace matrices (host arrays or DeviceMatrix) on domains shift_i * H_i.
+        -> (commitment[8], ProverData holding the bit-reversed LDEs)"""
+        if not evaluations:
+            raise ValueError("commit needs at least one matrix")
+        mats = [m if isinstance(m, DeviceMatrix) else self.ctx.upload(m) for m in evaluations]
+        if domain_shifts is None:
+            shifts = [GENERATOR_MONTY] * len(mats)
+        else:  # shift = GENERATOR / domain.shift  (canonical ints in, Montgomery out)
+            shifts = [monty_scalar(31 * pow(int(s), -1, P) % P) for s in domain_shifts]
+        arr = (C.c_void_p * len(mats))(*[m.h for m in mats])
+        sh = (C.c_uint32 * len(mats))(*shifts)
+        root = np.empty(DIGEST, np.uint32)
+        t = C.c_void_p()
+        self.ctx.check(self.ctx.lib.b200zk_lde_commit(self.ctx.h, arr, len(mats), self.config.log_blowup, sh, root.ctypes.data, C.byref(t)))
+        n = int(self.ctx.lib.b200zk_tree_num_mats(t))
+        ldes = [DeviceMatrix(self.ctx, C.c_void_p(self.ctx.lib.b200zk_tree_mat(t, i)), False) for i in range(n)]
+        return root, ProverData(self.ctx, t, ldes)
+
+    def get_evaluations_on_domain(self, prover_data: ProverData, idx: int) -> DeviceMatrix:
+        return prover_data.mats[idx]
