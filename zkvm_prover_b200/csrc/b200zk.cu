@@ -92,20 +92,26 @@ inline int log2u(uint64_t x) {
 int dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
     *out = nullptr;
     if (!bytes) bytes = 16;
-    cudaError_t e = cudaMalloc(out, bytes);
+    // stream-ordered pool allocation (release threshold = never): after warm-up an allocation costs
+    // microseconds instead of the tens of milliseconds cudaMalloc/cudaFree take for GB-sized buffers
+    cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return fail(ctx, B200ZK_ERR_OOM, "cudaMalloc(" + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        return fail(ctx, B200ZK_ERR_OOM, "cudaMallocAsync(" + std::to_string(bytes) + "): " + cudaGetErrorString(e));
     }
     return B200ZK_OK;
+}
+void dev_free(b200zk_ctx* ctx, void* p) {
+    if (!p) return;
+    if (ctx && ctx->stream) cudaFreeAsync(p, ctx->stream);
+    else cudaFree(p);
 }
 
 // ---------------------------------------------------------------------------------------------- twiddles
 int ensure_tab(b200zk_ctx* ctx, size_t words) {
     if (ctx->tab_words >= words) return B200ZK_OK;
     if (ctx->tab) {
-        CU(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->tab);
+        dev_free(ctx, ctx->tab);
         ctx->tab = nullptr;
         ctx->tab_words = 0;
     }
@@ -194,9 +200,11 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         if (blocks > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
         if (vec == 4) {
             CU(cudaFuncSetAttribute(ntt::pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(ntt::pass_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             ntt::pass_kernel<4><<<(uint32_t)blocks, ntt::THREADS, smem, ctx->stream>>>(p);
         } else {
             CU(cudaFuncSetAttribute(ntt::pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(ntt::pass_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             ntt::pass_kernel<1><<<(uint32_t)blocks, ntt::THREADS, smem, ctx->stream>>>(p);
         }
         LAUNCHED();
@@ -253,6 +261,14 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
         return B200ZK_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     if (cudaMalloc((void**)&ctx->d_small, 65536) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -351,11 +367,8 @@ uint32_t* b200zk_mat_device_ptr(const b200zk_mat* m) { return m ? m->d : nullptr
 void b200zk_mat_free(b200zk_ctx* ctx, b200zk_mat* m) {
     if (!m) return;
     if (m->owned && m->d) {
-        if (ctx) {
-            cudaSetDevice(ctx->device);
-            cudaStreamSynchronize(ctx->stream);
-        }
-        cudaFree(m->d);
+        if (ctx) cudaSetDevice(ctx->device);
+        dev_free(ctx, m->d);
     }
     delete m;
 }
@@ -532,7 +545,7 @@ int b200zk_poseidon2_permute(b200zk_ctx* ctx, uint32_t* h_states, uint64_t n) {
     if (e == cudaSuccess) rc = b200zk_poseidon2_permute_dev(ctx, d, n);
     if (e == cudaSuccess && rc == B200ZK_OK) e = cudaMemcpyAsync(h_states, d, n * 64, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    dev_free(ctx, d);
     if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     return rc;
 }
@@ -571,7 +584,7 @@ int b200zk_hash_rows(b200zk_ctx* ctx, const b200zk_mat* m, uint32_t* h_digests) 
     cudaError_t e = cudaSuccess;
     if (rc == B200ZK_OK) e = cudaMemcpyAsync(h_digests, d, m->rows * 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    dev_free(ctx, d);
     if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     return rc;
 }
@@ -599,7 +612,7 @@ int b200zk_compress_pairs(b200zk_ctx* ctx, const uint32_t* h_in, uint32_t* h_out
     if (e == cudaSuccess) rc = b200zk_compress_pairs_dev(ctx, d, d + 16 * n, n);
     if (e == cudaSuccess && rc == B200ZK_OK) e = cudaMemcpyAsync(h_out, d + 16 * n, n * 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    dev_free(ctx, d);
     if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     return rc;
 }
@@ -607,12 +620,9 @@ int b200zk_compress_pairs(b200zk_ctx* ctx, const uint32_t* h_in, uint32_t* h_out
 // ================================================================================================ Merkle
 void b200zk_tree_free(b200zk_ctx* ctx, b200zk_tree* t) {
     if (!t) return;
-    if (ctx) {
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-    }
-    cudaFree(t->d_digests);
-    cudaFree(t->d_open);
+    if (ctx) cudaSetDevice(ctx->device);
+    dev_free(ctx, t->d_digests);
+    dev_free(ctx, t->d_open);
     if (t->owns_mats)
         for (auto* m : t->mats) b200zk_mat_free(ctx, m);
     delete t;
@@ -769,7 +779,7 @@ int b200zk_merkle_open(b200zk_ctx* ctx, const b200zk_tree* t, uint64_t index, ui
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_rows, d, t->total_width * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && t->depth) e = cudaMemcpyAsync(h_path, d + t->total_width, 32ull * t->depth, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    dev_free(ctx, d);
     if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     return B200ZK_OK;
 }
@@ -817,7 +827,7 @@ int b200zk_merkle_verify(b200zk_ctx* ctx, const uint32_t* h_rows, const uint64_t
     uint32_t ok = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&ok, d + o_ok, 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
+    dev_free(ctx, d);
     if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     *h_ok = (int)ok;
     return B200ZK_OK;
@@ -841,8 +851,7 @@ int b200zk_chal_create(b200zk_ctx* ctx, b200zk_chal** out) {
 }
 void b200zk_chal_free(b200zk_ctx* ctx, b200zk_chal* c) {
     if (!c) return;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
-    cudaFree(c->d);
+    dev_free(ctx, c->d);
     delete c;
 }
 int b200zk_chal_observe(b200zk_ctx* ctx, b200zk_chal* c, const uint32_t* h_values, uint32_t n) {
@@ -1009,7 +1018,7 @@ int b200zk_fri_commit_phase(b200zk_ctx* ctx, const uint32_t* const* d_inputs, co
         const uint32_t* add = nullptr;
         if (next_in < n_inputs && lens[next_in] == len / 2) add = d_inputs[next_in++];
         rc = fold_launch(ctx, cur, len, d_betas + 4 * r, add, 1, ctx->tab + tab_per * r, nxt);
-        if (rc) { cudaFree(nxt); break; }
+        if (rc) { dev_free(ctx, nxt); break; }
         cur = nxt;
         owned_cur = nxt;
         len >>= 1;
@@ -1020,10 +1029,7 @@ int b200zk_fri_commit_phase(b200zk_ctx* ctx, const uint32_t* const* d_inputs, co
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     }
-    if (owned_cur) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(owned_cur);
-    }
+    if (owned_cur) dev_free(ctx, owned_cur);
     if (rc == B200ZK_OK && trees) {
         for (uint32_t r = 0; r < max_rounds; r++) trees[r] = made[r];
     } else {
@@ -1038,10 +1044,7 @@ int b200zk_dev_alloc(b200zk_ctx* ctx, uint64_t bytes, void** d_out) {
     CU(cudaSetDevice(ctx->device));
     return dev_alloc(ctx, bytes, d_out);
 }
-void b200zk_dev_free(b200zk_ctx* ctx, void* d) {
-    if (ctx) cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-}
+void b200zk_dev_free(b200zk_ctx* ctx, void* d) { dev_free(ctx, d); }
 int b200zk_dev_upload(b200zk_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes) {
     if (!ctx) return B200ZK_ERR_ARG;
     if (!d_dst || !h_src) return fail(ctx, B200ZK_ERR_ARG, "null pointer");

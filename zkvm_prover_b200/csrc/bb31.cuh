@@ -26,24 +26,35 @@ constexpr uint32_t GEN27 = 0x1a427a41u;    // canonical 31^15: generator of the 
 
 BB_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-BB_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
-#ifdef __CUDA_ARCH__
-    return __umulhi(a, b);
-#else
-    return (uint32_t)(((uint64_t)a * b) >> 32);
+// ---- pipe model (sm_100a, measured: tools/pipe_microbench.cu -> profiles/pipe_microbench_r01.txt)
+//   FMA pipe : IMAD and IMAD.WIDE 64 lanes/clk/SM, IMAD.HI 32 lanes/clk/SM
+//   ALU pipe : IADD3, VIADDMNMX, SHF, LOP3 64 lanes/clk/SM; the two pipes issue concurrently.
+// A Montgomery product costs 10 pipe-cycles per warp however it is written (IMAD.WIDE + IMAD + IMAD.HI + IADD3;
+// ptxas does not fuse a 64-bit addend into IMAD.WIDE for register operands), so the remaining lever is keeping both
+// pipes equally busy.  ptxas likes to turn plain additions into IMAD.IADD, which overloads the FMA pipe that already
+// carries the multiplies; `aadd` therefore pins an addition to the ALU pipe (a three-input IADD3 with an opaque zero
+// from constant memory -- IMAD cannot express it), `fadd` pins one to the FMA pipe (a*1+b with an opaque one).
+#ifdef __CUDACC__
+static __device__ __constant__ uint32_t K_ONE = 1u;
+static __device__ __constant__ uint32_t K_ZERO = 0u;
 #endif
-}
-BB_HD int32_t mulhi32(int32_t a, int32_t b) {
 #ifdef __CUDA_ARCH__
-    return __mulhi(a, b);
+BB_HD uint32_t fadd(uint32_t a, uint32_t b) { return a * K_ONE + b; }
+BB_HD uint32_t aadd(uint32_t a, uint32_t b) { return a + b + K_ZERO; }
+BB_HD uint32_t asub(uint32_t a, uint32_t b) { return a - b + K_ZERO; }
+BB_HD uint64_t fadd64(uint64_t acc, uint32_t x) { return (uint64_t)x * K_ONE + acc; }
+BB_HD int32_t mulhi32(int32_t a, int32_t b) { return __mulhi(a, b); }
 #else
-    return (int32_t)(((int64_t)a * b) >> 32);
+BB_HD uint32_t fadd(uint32_t a, uint32_t b) { return a + b; }
+BB_HD uint32_t aadd(uint32_t a, uint32_t b) { return a + b; }
+BB_HD uint32_t asub(uint32_t a, uint32_t b) { return a - b; }
+BB_HD uint64_t fadd64(uint64_t acc, uint32_t x) { return acc + x; }
+BB_HD int32_t mulhi32(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * b) >> 32); }
 #endif
-}
 
 // canonical [0,p) x [0,p) -> [0,p)
-BB_HD uint32_t add(uint32_t a, uint32_t b) { uint32_t s = a + b; return umin32(s, s - P); }
-BB_HD uint32_t sub(uint32_t a, uint32_t b) { uint32_t d = a - b; return umin32(d, d + P); }
+BB_HD uint32_t add(uint32_t a, uint32_t b) { uint32_t s = aadd(a, b); return umin32(s, s - P); }
+BB_HD uint32_t sub(uint32_t a, uint32_t b) { uint32_t d = asub(a, b); return umin32(d, d + P); }
 BB_HD uint32_t neg(uint32_t a) { return a ? P - a : 0u; }
 BB_HD uint32_t dbl(uint32_t a) { return add(a, a); }
 // any value < 2p -> [0,p)
@@ -51,26 +62,21 @@ BB_HD uint32_t red2p(uint32_t a) { return umin32(a, a - P); }
 // signed representative in (-p,p) (as int32 bits) -> [0,p)
 BB_HD uint32_t canon(int32_t r) { uint32_t u = (uint32_t)r; return umin32(u, u + P); }
 
-// Montgomery reduction of t < p*2^32 -> [0,p)
-BB_HD uint32_t reduce(uint64_t t) {
-    uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
-    uint32_t q = lo * MU;
-    uint32_t qh = umulhi32(q, P);
-    uint32_t r = hi - qh;
-    return umin32(r, r + P);
-}
-// a < 2^32, b < p (or a*b < p*2^32) -> [0,p)
-BB_HD uint32_t mul(uint32_t a, uint32_t b) { return reduce((uint64_t)a * b); }
-
 // signed Montgomery product: |a*b| < 2^31 * p  ->  representative in (-p, p), no correction step.
-// Used for multiply chains (x^7) where intermediates only feed further multiplies.
+//   t = a*b ; q = lo(t) * p^-1 (mod 2^32, signed) ; (t - q*p) / 2^32 = hi(t) - hi(q*p)  (the low words cancel)
 BB_HD int32_t smul(int32_t a, int32_t b) {
-    int64_t t = (int64_t)a * b;
-    uint32_t lo = (uint32_t)t;
-    int32_t hi = (int32_t)(t >> 32);
-    int32_t q = (int32_t)(lo * MU);
+    int64_t t = (int64_t)a * (int64_t)b;
+    int32_t q = (int32_t)((uint32_t)t * MU);
     int32_t qh = mulhi32(q, (int32_t)P);
-    return hi - qh;
+    return (int32_t)asub((uint32_t)(t >> 32), (uint32_t)qh);
+}
+// canonical operands (any pair with |a*b| < 2^31 p, taken as signed) -> [0,p)
+BB_HD uint32_t mul(uint32_t a, uint32_t b) { return canon(smul((int32_t)a, (int32_t)b)); }
+// Montgomery reduction of 0 <= t < 2^31 * p -> [0,p)
+BB_HD uint32_t reduce(uint64_t t) {
+    int32_t q = (int32_t)((uint32_t)t * MU);
+    int32_t qh = mulhi32(q, (int32_t)P);
+    return canon((int32_t)((uint32_t)(t >> 32) - (uint32_t)qh));
 }
 
 BB_HD uint32_t to_monty(uint32_t x) { return mul(x % P, R2); }

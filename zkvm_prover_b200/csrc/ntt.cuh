@@ -86,7 +86,7 @@ __device__ __forceinline__ void radix_round(uint32_t* sm, const uint32_t* sm_tw,
                 for (int c = 0; c < VEC; c++) {
                     uint32_t a = x[q].v[c], b = x[q + half].v[c];
                     x[q].v[c] = bb::add(a, b);
-                    x[q + half].v[c] = bb::mul(a - b + bb::P, w);
+                    x[q + half].v[c] = bb::canon(bb::smul((int32_t)(a - b), (int32_t)w));  // a-b in (-p,p) as signed
                 }
             }
         }

@@ -34,12 +34,30 @@ constexpr uint32_t RC_CANON[141] = {P2_RC_LIST};
 __device__ __constant__ uint32_t RC_CANON_DEV[141] = {P2_RC_LIST};
 #endif
 
-// round constant idx in Montgomery form minus p, as a signed value in [-p, 0): state + rcs in [-p, p)
-template <int IDX>
-struct RC {
-    static constexpr uint32_t monty = (uint32_t)((((uint64_t)RC_CANON[IDX]) << 32) % bb::P);
-    static constexpr int32_t shifted = (int32_t)monty - (int32_t)bb::P;
+// round constants in Montgomery form minus p, as signed values in [-p, 0): state + rc lands in [-p, p)
+struct Tables {
+    int32_t ext[8][16];
+    int32_t in[13];
 };
+constexpr Tables make_tables() {
+    Tables t{};
+    for (int r = 0; r < 8; r++)
+        for (int i = 0; i < 16; i++) {
+            const int idx = (r < 4 ? 16 * r : 77 + 16 * (r - 4)) + i;
+            t.ext[r][i] = (int32_t)((((uint64_t)RC_CANON[idx]) << 32) % bb::P) - (int32_t)bb::P;
+        }
+    for (int r = 0; r < 13; r++) t.in[r] = (int32_t)((((uint64_t)RC_CANON[64 + r]) << 32) % bb::P) - (int32_t)bb::P;
+    return t;
+}
+#ifdef __CUDACC__
+static __device__ __constant__ Tables T_DEV = make_tables();
+#endif
+static constexpr Tables T_HOST = make_tables();
+#ifdef __CUDA_ARCH__
+#define P2_TAB p2::T_DEV
+#else
+#define P2_TAB p2::T_HOST
+#endif
 
 // x in [-p, p) (signed) -> x^7 canonical
 BB_HD uint32_t sbox7(int32_t x) {
@@ -49,39 +67,53 @@ BB_HD uint32_t sbox7(int32_t x) {
     return bb::canon(bb::smul(x3, x4));
 }
 
-// circ(2*M4, M4, M4, M4) with M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]] (p3-poseidon2 mds_light_permutation)
+// ---- tuning knobs (pipe assignment; see bb31.cuh "pipe model").  Defaults are the measured best.
+#ifndef P2_RC_FMA
+#define P2_RC_FMA 0      // round-constant additions on the FMA pipe (1) or ALU pipe (0)
+#endif
+#ifndef P2_MDS_MODE
+#define P2_MDS_MODE 3    // how many of the linear-layer additions are steered to the FMA pipe (0 none .. 3)
+#endif
+#ifndef P2_INT_MODE
+#define P2_INT_MODE 1    // internal layer: 0 = 64-bit IMAD.WIDE formulation, 1 = ALU formulation (doublings / 32-bit shifts)
+#endif
+
+BB_HD uint32_t add_f(uint32_t a, uint32_t b) { uint32_t s = bb::fadd(a, b); return bb::umin32(s, s - bb::P); }
+#define P2_ADD_LVL(lvl, a, b) ((P2_MDS_MODE >= (lvl)) ? add_f((a), (b)) : bb::add((a), (b)))
+
+// circ(2*M4, M4, M4, M4) with M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]] (p3-poseidon2 mds_light_permutation);
+// the 4x4 block uses the 11-addition schedule (t01, t23, t0123, t01123, t01233, two doublings, four sums).
 BB_HD void mds_light(uint32_t (&s)[16]) {
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
         uint32_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
-        uint32_t t01 = bb::red2p(x0 + x1);
-        uint32_t t23 = bb::red2p(x2 + x3);
-        uint32_t t = bb::add(t01, t23);
-        uint32_t a = bb::add(t01, x1);               // x0 + 2 x1
-        uint32_t b = bb::add(t23, x3);               // x2 + 2 x3
-        s[c] = bb::add(t, a);                        // 2x0 + 3x1 + x2 + x3
-        s[c + 2] = bb::add(t, b);                    // x0 + x1 + 2x2 + 3x3
-        s[c + 1] = bb::add(bb::add(t, x1), bb::dbl(x2));  // x0 + 2x1 + 3x2 + x3
-        s[c + 3] = bb::add(bb::add(t, x3), bb::dbl(x0));  // 3x0 + x1 + x2 + 2x3
+        uint32_t t01 = P2_ADD_LVL(1, x0, x1);
+        uint32_t t23 = P2_ADD_LVL(1, x2, x3);
+        uint32_t t0123 = bb::add(t01, t23);
+        uint32_t t01123 = bb::add(t0123, x1);
+        uint32_t t01233 = bb::add(t0123, x3);
+        uint32_t d0 = P2_ADD_LVL(2, x0, x0), d2 = P2_ADD_LVL(2, x2, x2);
+        s[c + 3] = bb::add(t01233, d0);           // 3x0 + x1 + x2 + 2x3
+        s[c + 1] = bb::add(t01123, d2);           // x0 + 2x1 + 3x2 + x3
+        s[c] = bb::add(t01123, t01);              // 2x0 + 3x1 + x2 + x3
+        s[c + 2] = bb::add(t01233, t23);          // x0 + x1 + 2x2 + 3x3
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        uint32_t t = bb::add(bb::red2p(s[k] + s[4 + k]), bb::red2p(s[8 + k] + s[12 + k]));
+        uint32_t t = bb::add(bb::add(s[k], s[4 + k]), bb::add(s[8 + k], s[12 + k]));
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) s[j + k] = bb::add(s[j + k], t);
+        for (int j = 0; j < 16; j += 4) s[j + k] = P2_ADD_LVL(3, s[j + k], t);
     }
 }
 
-template <int BASE>
-BB_HD void external_round(uint32_t (&s)[16]) {
-#define P2_SB(i) s[i] = sbox7((int32_t)s[i] + RC<BASE + i>::shifted);
-    P2_SB(0) P2_SB(1) P2_SB(2) P2_SB(3) P2_SB(4) P2_SB(5) P2_SB(6) P2_SB(7)
-    P2_SB(8) P2_SB(9) P2_SB(10) P2_SB(11) P2_SB(12) P2_SB(13) P2_SB(14) P2_SB(15)
-#undef P2_SB
+BB_HD void external_round(uint32_t (&s)[16], const int32_t* rc) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = sbox7((int32_t)(P2_RC_FMA ? bb::fadd(s[i], (uint32_t)rc[i]) : bb::aadd(s[i], (uint32_t)rc[i])));
     mds_light(s);
 }
 
-// sum + c*x for a small integer c in [-4, 4], everything canonical
+#if P2_INT_MODE == 0
+// sum + c*x for a small integer c in [-4, 4], everything canonical (64-bit multiply-accumulate formulation)
 template <int C>
 BB_HD uint32_t lin_small(uint32_t sum, uint32_t x) {
     constexpr uint64_t OFF = C < 0 ? (uint64_t)(-C) * bb::P : 0ull;
@@ -90,58 +122,82 @@ BB_HD uint32_t lin_small(uint32_t sum, uint32_t x) {
     uint32_t r = (uint32_t)u - q * bb::P;                                    // < 2^31 + 4 * 2^27 < 2p
     return bb::red2p(r);
 }
-
-template <int IDX>
-BB_HD void internal_round(uint32_t (&s)[16]) {
-    s[0] = sbox7((int32_t)s[0] + RC<IDX>::shifted);
-    // 16-term sum: pair sums fit in 32 bits, the rest accumulates in 64 bits; one reduction
-    uint64_t acc = (uint64_t)(s[0] + s[1]) + (uint64_t)(s[2] + s[3]) + (uint64_t)(s[4] + s[5]) + (uint64_t)(s[6] + s[7]) +
-                   (uint64_t)(s[8] + s[9]) + (uint64_t)(s[10] + s[11]) + (uint64_t)(s[12] + s[13]) + (uint64_t)(s[14] + s[15]);
+template <int K>
+BB_HD uint32_t div2(uint32_t x) { return bb::div2exp<K>(x); }
+BB_HD uint32_t sum16(const uint32_t (&s)[16]) {
+    // pair sums fit in 32 bits, the rest accumulates in 64 bits; one reduction
+    uint64_t acc = (uint64_t)(s[0] + s[1]);
+    acc = bb::fadd64(acc, s[2] + s[3]);
+    acc = bb::fadd64(acc, s[4] + s[5]);
+    acc = bb::fadd64(acc, s[6] + s[7]);
+    uint64_t acc2 = (uint64_t)(s[8] + s[9]);
+    acc2 = bb::fadd64(acc2, s[10] + s[11]);
+    acc2 = bb::fadd64(acc2, s[12] + s[13]);
+    acc2 = bb::fadd64(acc2, s[14] + s[15]);
+    acc += acc2;
     uint32_t q = (uint32_t)(acc >> 31);          // < 16
     uint32_t r = (uint32_t)acc - q * bb::P;      // < 2^31 + 15 * 2^27 < 2^32
-    uint32_t sum = bb::red2p(bb::red2p(r));      // r < 2.07 p
+    return bb::red2p(bb::red2p(r));              // r < 2.07 p
+}
+#else
+// ALU formulation: the FMA pipe is saturated by the S-box multiplies, so small multiples are built from canonical
+// doublings and the exact divisions by 2^K use 32-bit arithmetic only:
+//   x / 2^K = ((x + 2^K - 1) >> K) + m * (15 << (27 - K)),  m = (-x) mod 2^K     (p = 15 * 2^27 + 1)
+template <int C>
+BB_HD uint32_t lin_small(uint32_t sum, uint32_t x) {
+    constexpr int A = C < 0 ? -C : C;
+    uint32_t d = bb::dbl(x);
+    uint32_t m = A == 2 ? d : (A == 3 ? bb::add(d, x) : bb::dbl(d));
+    return C < 0 ? bb::sub(sum, m) : bb::add(sum, m);
+}
+template <int K>
+BB_HD uint32_t div2(uint32_t x) {
+    constexpr uint32_t MASK = (1u << K) - 1u;
+    uint32_t m = (0u - x) & MASK;
+    return ((x + MASK) >> K) + m * (15u << (27 - K));
+}
+BB_HD uint32_t sum16(const uint32_t (&s)[16]) {
+    uint32_t a0 = bb::add(s[0], s[1]), a1 = bb::add(s[2], s[3]), a2 = bb::add(s[4], s[5]), a3 = bb::add(s[6], s[7]);
+    uint32_t a4 = bb::add(s[8], s[9]), a5 = bb::add(s[10], s[11]), a6 = bb::add(s[12], s[13]), a7 = bb::add(s[14], s[15]);
+    return bb::add(bb::add(bb::add(a0, a1), bb::add(a2, a3)), bb::add(bb::add(a4, a5), bb::add(a6, a7)));
+}
+#endif
+
+BB_HD void internal_round(uint32_t (&s)[16], int32_t rc) {
+    s[0] = sbox7((int32_t)(P2_RC_FMA ? bb::fadd(s[0], (uint32_t)rc) : bb::aadd(s[0], (uint32_t)rc)));
+    const uint32_t sum = sum16(s);
     s[0] = lin_small<-2>(sum, s[0]);
     s[1] = bb::add(sum, s[1]);
     s[2] = lin_small<2>(sum, s[2]);
-    s[3] = bb::add(sum, bb::div2exp<1>(s[3]));
+    s[3] = bb::add(sum, div2<1>(s[3]));
     s[4] = lin_small<3>(sum, s[4]);
     s[5] = lin_small<4>(sum, s[5]);
-    s[6] = bb::sub(sum, bb::div2exp<1>(s[6]));
+    s[6] = bb::sub(sum, div2<1>(s[6]));
     s[7] = lin_small<-3>(sum, s[7]);
     s[8] = lin_small<-4>(sum, s[8]);
-    s[9] = bb::add(sum, bb::div2exp<8>(s[9]));
-    s[10] = bb::add(sum, bb::div2exp<2>(s[10]));
-    s[11] = bb::add(sum, bb::div2exp<3>(s[11]));
-    s[12] = bb::add(sum, bb::div2exp<27>(s[12]));
-    s[13] = bb::sub(sum, bb::div2exp<8>(s[13]));
-    s[14] = bb::sub(sum, bb::div2exp<4>(s[14]));
-    s[15] = bb::sub(sum, bb::div2exp<27>(s[15]));
+    s[9] = bb::add(sum, div2<8>(s[9]));
+    s[10] = bb::add(sum, div2<2>(s[10]));
+    s[11] = bb::add(sum, div2<3>(s[11]));
+    s[12] = bb::add(sum, div2<27>(s[12]));
+    s[13] = bb::sub(sum, div2<8>(s[13]));
+    s[14] = bb::sub(sum, div2<4>(s[14]));
+    s[15] = bb::sub(sum, div2<27>(s[15]));
 }
 
-// canonical Montgomery state in, canonical out
+// canonical Montgomery state in, canonical out.  The round loops are deliberately NOT unrolled: the fully
+// unrolled body (~90 KB of SASS) thrashed the instruction cache (ncu: `no_instruction` was the top stall);
+// rolled, the whole permutation is ~10 KB and the round constants come from constant memory.
 BB_HD void permute(uint32_t (&s)[16]) {
     mds_light(s);
-    external_round<0>(s);
-    external_round<16>(s);
-    external_round<32>(s);
-    external_round<48>(s);
-    internal_round<64>(s);
-    internal_round<65>(s);
-    internal_round<66>(s);
-    internal_round<67>(s);
-    internal_round<68>(s);
-    internal_round<69>(s);
-    internal_round<70>(s);
-    internal_round<71>(s);
-    internal_round<72>(s);
-    internal_round<73>(s);
-    internal_round<74>(s);
-    internal_round<75>(s);
-    internal_round<76>(s);
-    external_round<77>(s);
-    external_round<93>(s);
-    external_round<109>(s);
-    external_round<125>(s);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) external_round(s, P2_TAB.ext[4 * half + r]);
+        if (half == 0) {
+#pragma unroll 1
+            for (int r = 0; r < 13; r++) internal_round(s, P2_TAB.in[r]);
+        }
+    }
 }
 
 // straightforward variant (generic Montgomery multiplies everywhere); kept as an in-library cross-check
