@@ -1,0 +1,111 @@
+"""Multi-GPU layer: only where the path shards.
+
+* segments / independent proofs: `segment_assignment` -- replicas, no data-path collective; roots gathered at the end.
+* one wide matrix: `sharded_lde_commit` -- columns sharded for the LDE (columns are independent), one all-to-all to
+  row blocks, per-rank subtree over its contiguous (bit-reversed-order) rows, all-gather of the G subtree roots (the
+  "cap"), the top log2(G) levels compressed redundantly on every rank.  The root is bit-identical to the single-GPU root.
+
+The collective plumbing is torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).  The arithmetic comes
+from an `ops` object: `GpuOps` (the CUDA library) in production; the CPU tests inject an oracle-backed one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def segment_assignment(n_segments: int, world: int):
+    """round-robin continuation segments (or chunk tasks) over ranks: independent units, no collective"""
+    return [[s for s in range(n_segments) if s % world == r] for r in range(world)]
+
+
+def _all_to_all_equal(recv: torch.Tensor, send: torch.Tensor, group=None):
+    """recv[s] <- block `rank` of rank s's `send` (equal splits along dim 0)"""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    try:
+        if dist.get_backend(group) != "gloo":
+            dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+            return
+    except Exception:
+        pass
+    ops = []
+    recv[rank].copy_(send[rank])
+    for peer in range(world):
+        if peer == rank:
+            continue
+        ops.append(dist.P2POp(dist.isend, send[peer].contiguous(), peer, group))
+        ops.append(dist.P2POp(dist.irecv, recv[peer], peer, group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+class GpuOps:
+    """arithmetic backend = libb200zk on this rank's GPU; tensors are int32 CUDA tensors viewed as BabyBear u32"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.device = torch.device("cuda", ctx.device)
+
+    def to_device(self, arr) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint32).view(np.int32)).to(self.device)
+
+    def lde(self, local: torch.Tensor, added_bits: int, shift: int) -> torch.Tensor:
+        n, w = local.shape
+        out = torch.empty((n << added_bits, w), dtype=torch.int32, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        src = self.ctx.wrap(local.data_ptr(), n, w, keepalive=local)
+        dst = self.ctx.wrap(out.data_ptr(), n << added_bits, w, keepalive=out)
+        self.ctx.check(self.ctx.lib.b200zk_coset_lde_batch_into(self.ctx.h, src.h, added_bits, shift, 1, dst.h))
+        self.ctx.sync()
+        return out
+
+    def subtree_root(self, chunks) -> np.ndarray:
+        torch.cuda.current_stream(self.device).synchronize()
+        mats = [self.ctx.wrap(c.data_ptr(), c.shape[0], c.shape[1], keepalive=c) for c in chunks]
+        arr = (C.c_void_p * len(mats))(*[m.h for m in mats])
+        root = np.empty(8, np.uint32)
+        t = C.c_void_p()
+        self.ctx.check(self.ctx.lib.b200zk_merkle_commit(self.ctx.h, arr, len(mats), 0, root.ctypes.data, C.byref(t)))
+        self.ctx.lib.b200zk_tree_free(self.ctx.h, t)
+        return root
+
+    def compress(self, pairs: np.ndarray) -> np.ndarray:
+        p = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 16)
+        out = np.empty((p.shape[0], 8), np.uint32)
+        self.ctx.check(self.ctx.lib.b200zk_compress_pairs(self.ctx.h, p.ctypes.data, out.ctypes.data, p.shape[0]))
+        return out
+
+
+def combine_cap(cap: np.ndarray, compress) -> np.ndarray:
+    """cap: (G, 8) subtree roots in rank order (G a power of two) -> Merkle root of the whole tree"""
+    layer = np.ascontiguousarray(cap, dtype=np.uint32)
+    while layer.shape[0] > 1:
+        layer = compress(layer.reshape(-1, 16))
+    return layer[0]
+
+
+def sharded_lde_commit(ops, local_cols, added_bits: int, shift: int, group=None):
+    """Every rank holds a column shard (N x W/G, same N and W/G everywhere) of one trace matrix.
+    Returns (root[8] -- identical on all ranks and to the single-GPU commit of the full LDE --, cap (G,8))."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world & (world - 1):
+        raise ValueError("the number of ranks must be a power of two")
+    local = local_cols if isinstance(local_cols, torch.Tensor) else ops.to_device(local_cols)
+    lde = ops.lde(local, added_bits, shift)                 # (M, Wg), rows in bit-reversed order
+    m, wg = lde.shape
+    if m % world:
+        raise ValueError("LDE height must be divisible by the number of ranks")
+    mg = m // world
+    send = lde.view(world, mg, wg)                          # row block r goes to rank r
+    recv = torch.empty_like(send)
+    _all_to_all_equal(recv, send, group)                    # recv[s] = my row block of rank s's columns
+    root_local = ops.subtree_root([recv[s] for s in range(world)])  # sponge over the G column shards in order
+    cap_t = [torch.zeros(8, dtype=torch.int64, device=lde.device) for _ in range(world)]
+    dist.all_gather(cap_t, torch.from_numpy(root_local.astype(np.int64)).to(lde.device), group=group)
+    cap = np.stack([c.cpu().numpy().astype(np.uint32) for c in cap_t])
+    return combine_cap(cap, ops.compress), cap
