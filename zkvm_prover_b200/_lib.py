@@ -10,7 +10,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200zk.so")
+LIB_PATH = os.environ.get("B200ZK_LIB_PATH", os.path.join(HERE, "libb200zk.so"))  # override only for A/B kernel experiments
 HEADER = os.path.join(os.path.dirname(HERE), "include", "b200zk.h")
 
 OK, ERR_CUDA, ERR_OOM, ERR_SHAPE, ERR_ARG = 0, -1, -2, -3, -4

@@ -1,10 +1,12 @@
 // C ABI of libb200zk (see include/b200zk.h).  Host-side orchestration only: argument checking, device
 // memory, pass planning and kernel launches on the context's stream.  No CPU arithmetic path exists here:
 // every field operation on user data happens in the kernels of ntt.cuh / merkle.cuh / fri.cuh.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -36,6 +38,8 @@ struct b200zk_ctx {
     size_t tab_words = 0;
     uint32_t* d_small = nullptr;  // 64 KB of small device scratch (roots, betas, flags)
     int max_smem_optin = 0;
+    int num_sms = 148;
+    void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), null if unavailable
 };
 struct b200zk_mat {
     uint32_t* d = nullptr;
@@ -151,13 +155,42 @@ int ensure_local(b200zk_ctx* ctx, int inverse, int K) {
 }
 
 // split n stages into passes
-std::vector<int> make_plan(int n) {
+std::vector<int> make_plan(int n, int kmax_force = 0) {
     std::vector<int> plan;
     if (n <= 0) return plan;
     int kmax = (n > 2 * KMAX_SMALL && n <= 2 * KMAX_BIG) ? KMAX_BIG : KMAX_SMALL;
+    if (kmax_force) kmax = kmax_force;
     int m = (n + kmax - 1) / kmax;
     for (int i = 0; i < m; i++) plan.push_back(n / m + (i < n % m ? 1 : 0));
     return plan;
+}
+
+
+static_assert(sizeof(ntt::TensorMap) == sizeof(CUtensorMap), "TensorMap must mirror CUtensorMap");
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 4-D view of the rows a pass touches: {column, low, t, high}; one box = one tile
+int make_pass_map(b200zk_ctx* ctx, const uint32_t* base, uint32_t width, int n, int s0, int K, int lc, ntt::TensorMap* out) {
+    const int L = n - s0 - K;
+    cuuint64_t dims[4] = {width, 1ull << L, 1ull << K, 1ull << s0};
+    cuuint64_t strides[3] = {(cuuint64_t)width * 4, ((cuuint64_t)width * 4) << L, ((cuuint64_t)width * 4) << (L + K)};
+    cuuint32_t box[4] = {1u << lc, 1, 1u << K, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)base, dims, strides, box,
+                                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, B200ZK_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return B200ZK_OK;
+}
+
+bool tma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200ZK_NTT_TMA");  // experiment knob: 0 forces the plain pass kernel
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
 }
 
 struct Scale {
@@ -169,10 +202,10 @@ struct Scale {
 // last pass scatters into dst_final (which must not alias its source).
 int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t* dst_final, int n, uint32_t width, int inverse, Scale pre,
                   Scale post, int out_natural) {
-    std::vector<int> plan = make_plan(n);
     TRY(ensure_roots(ctx, n));
     const int vec = (width % 4 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)work % 16 == 0) && ((uintptr_t)dst_final % 16 == 0)) ? 4 : 1;
-    const uint32_t col_tiles = (width + ntt::TILE_COLS - 1) / ntt::TILE_COLS;
+    const bool tma_ok = vec == 4 && ctx->encode_tiled && tma_enabled();
+    std::vector<int> plan = make_plan(n, tma_ok ? ntt::TMA_MAX_K : 0);
     int s0 = 0;
     for (size_t i = 0; i < plan.size(); i++) {
         const int K = plan[i];
@@ -185,6 +218,13 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         p.n = n;
         p.s0 = s0;
         p.K = K;
+        // column tile: 2^14 elements per tile, at most 128 columns, no wider than the matrix needs
+        int lc = std::min(ntt::TILE_ELEMS_LOG - K, ntt::MAX_TILE_COLS_LOG);
+        while (lc > (vec == 4 ? 2 : 0) && (1u << (lc - 1)) >= width) lc--;
+        if (K == KMAX_BIG) lc = 5;  // the two-pass plan for n = 19, 20 keeps its 128 KB tile
+        p.lc = lc;
+        const uint32_t tile_cols = 1u << lc;
+        const uint32_t col_tiles = (width + tile_cols - 1) / tile_cols;
         p.inverse = inverse;
         p.tw_local = ctx->tw_local[inverse][K];
         p.tw_lo = ctx->tw_lo[n];
@@ -194,8 +234,32 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         p.post_lo = last ? post.lo : nullptr;
         p.post_hi = last ? post.hi : nullptr;
         p.out_natural = last ? out_natural : 0;
+        {
+            const char* e = getenv("B200ZK_NTT_PREFETCH");  // experiment knob: CTAs of look-ahead (0 disables)
+            p.prefetch_dist = e ? (uint32_t)atoi(e) : 148u; // measured best look-ahead (profiles/ntt_tuning_r01.txt)
+        }
         const uint64_t R = 1ull << K;
-        const size_t smem = (R * ntt::TILE_COLS + std::max<uint64_t>(R / 2, 1) + R) * 4;
+        if (tma_ok && K <= ntt::TMA_MAX_K && !p.out_natural && !p.post_lo) {
+            // persistent warp-specialised TMA pass: 2^13-element tiles, 3-stage ring, 2 CTAs per SM
+            int tl = std::min(ntt::TMA_TILE_LOG - K, ntt::MAX_TILE_COLS_LOG);
+            while (tl > 2 && (1u << (tl - 1)) >= width) tl--;
+            p.lc = tl;
+            const uint32_t tcols = 1u << tl;
+            const uint64_t tiles = ((1ull << n) >> K) * ((width + tcols - 1) / tcols);
+            if (tiles > 0xffffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
+            ntt::TensorMap in_map, out_map;
+            TRY(make_pass_map(ctx, p.in, width, n, s0, K, tl, &in_map));
+            TRY(make_pass_map(ctx, p.out, width, n, s0, K, tl, &out_map));
+            const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
+            CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+            CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, 2ull * ctx->num_sms);
+            ntt::pass_kernel_tma<<<grid, ntt::TMA_THREADS, tsm, ctx->stream>>>(in_map, out_map, p, (uint32_t)tiles);
+            LAUNCHED();
+            s0 += K;
+            continue;
+        }
+        const size_t smem = (R * tile_cols + std::max<uint64_t>(R / 2, 1) + R) * 4;
         const uint64_t blocks = ((1ull << n) >> K) * col_tiles;
         if (blocks > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
         if (vec == 4) {
@@ -261,6 +325,13 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
         return B200ZK_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) ctx->encode_tiled = fn;
+        cudaGetLastError();
+    }
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

@@ -17,8 +17,15 @@
 
 namespace ntt {
 
-constexpr int TILE_COLS = 32;
-constexpr int THREADS = 512;
+constexpr int TILE_ELEMS_LOG = 14;  // a tile is 2^14 elements (64 KB): 2^K rows x 2^(14-K) columns, so all 512 threads have a radix-8 group
+constexpr int MAX_TILE_COLS_LOG = 7;  // at most 128 columns (512 B row segments)
+#ifndef NTT_THREADS
+#define NTT_THREADS 512
+#endif
+#ifndef NTT_MIN_CTAS
+#define NTT_MIN_CTAS 2
+#endif
+constexpr int THREADS = NTT_THREADS;
 constexpr int LO_BITS = 12;  // two-level power tables: x^e = hi[e >> 12] * lo[e & 4095]
 
 struct PassParams {
@@ -28,6 +35,7 @@ struct PassParams {
     int n;                // log2 of the transform size
     int s0;               // first DIF stage done by this pass
     int K;                // stages in this pass (tile = 2^K rows)
+    int lc;               // log2 of the tile's column count (tile = 2^K rows x 2^lc columns)
     int inverse;          // use inverse roots
     const uint32_t* tw_local;  // 2^(K-1): w_{2^K}^(+-i)
     const uint32_t* tw_lo;     // w_N^i, i < 2^min(n,12)      (forward roots; inverse uses N - e)
@@ -37,6 +45,7 @@ struct PassParams {
     const uint32_t* post_lo;   // optional (last pass only): multiply logical output index j likewise
     const uint32_t* post_hi;
     int out_natural;      // last pass only: write logical index j = bitrev_n(position) to row j
+    uint32_t prefetch_dist;  // CTAs resident at once: each CTA prefetches (to L2) the tile of block blockIdx.x + prefetch_dist
 };
 
 template <int VEC>
@@ -60,26 +69,49 @@ __device__ __forceinline__ uint32_t pow2level(const uint32_t* lo, const uint32_t
 }
 
 // k stages (radix 2^k) at local stage u of the 2^K-point DIF, on registers; sm = tile [2^K][TILE_COLS]
-template <int k, int VEC>
-__device__ __forceinline__ void radix_round(uint32_t* sm, const uint32_t* sm_tw, int K, int u, int tid) {
-    constexpr int LANES = TILE_COLS / VEC;  // threads per row
+// LAST: this round ends the tile's DIF (lowbits == 0), so the twiddle index of a butterfly depends only on q and the
+// butterflies with (q & (half-1)) == 0 multiply by w^0 = 1: they are done as plain subtractions (7 of the 12 butterflies
+// of a radix-8 round).
+template <int k, int VEC, bool LAST, int NT = THREADS>
+__device__ __forceinline__ void radix_round(uint32_t* sm, const uint32_t* sm_tw, int K, int lc, int u, int tid, const uint32_t* fac_pre = nullptr,
+                                            const uint32_t* fac_post = nullptr) {
+    constexpr int LV = VEC == 4 ? 2 : 0;
+    const int ll = lc - LV;                 // log2(threads per row)
+    const int TILE_COLS = 1 << lc;
     constexpr int R = 1 << k;
     const int lowbits = K - u - k;
-    const int groups = (1 << (K - k)) * LANES;
-    for (int gi = tid; gi < groups; gi += THREADS) {
-        const int lane = gi % LANES;
-        const int g = gi / LANES;
+    const int groups = 1 << (K - k + ll);
+    for (int gi = tid; gi < groups; gi += NT) {
+        const int lane = gi & ((1 << ll) - 1);
+        const int g = gi >> ll;
         const int highpart = g >> lowbits, lowpart = g & ((1 << lowbits) - 1);
         const int base = (highpart << (K - u)) + lowpart;
         Vec<VEC> x[R];
 #pragma unroll
         for (int q = 0; q < R; q++) x[q].load(sm + (base + (q << lowbits)) * TILE_COLS + lane * VEC);
+        if (fac_pre) {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const uint32_t f = fac_pre[base + (q << lowbits)];
+#pragma unroll
+                for (int c = 0; c < VEC; c++) x[q].v[c] = bb::mul(x[q].v[c], f);
+            }
+        }
 #pragma unroll
         for (int v = 0; v < k; v++) {
             const int half = 1 << (k - 1 - v);
 #pragma unroll
             for (int q = 0; q < R; q++) {
                 if (q & half) continue;
+                if (LAST && (q & (half - 1)) == 0) {
+#pragma unroll
+                    for (int c = 0; c < VEC; c++) {
+                        uint32_t a = x[q].v[c], b = x[q + half].v[c];
+                        x[q].v[c] = bb::add(a, b);
+                        x[q + half].v[c] = bb::sub(a, b);
+                    }
+                    continue;
+                }
                 const int e = (((q & (half - 1)) << lowbits) + lowpart) << (u + v);
                 const uint32_t w = sm_tw[e];
 #pragma unroll
@@ -90,15 +122,25 @@ __device__ __forceinline__ void radix_round(uint32_t* sm, const uint32_t* sm_tw,
                 }
             }
         }
+        if (fac_post) {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const uint32_t f = fac_post[base + (q << lowbits)];
+#pragma unroll
+                for (int c = 0; c < VEC; c++) x[q].v[c] = bb::mul(x[q].v[c], f);
+            }
+        }
 #pragma unroll
         for (int q = 0; q < R; q++) x[q].store(sm + (base + (q << lowbits)) * TILE_COLS + lane * VEC);
     }
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassParams p) {
+__global__ void __launch_bounds__(THREADS, NTT_MIN_CTAS) pass_kernel(const PassParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
-    constexpr int LANES = TILE_COLS / VEC;
+    constexpr int LV = VEC == 4 ? 2 : 0;
+    const int lc = p.lc, ll = lc - LV;
+    const int TILE_COLS = 1 << lc, LANES = 1 << ll;
     const int K = p.K, n = p.n, s0 = p.s0;
     const int L = n - s0 - K;
     const int R = 1 << K;
@@ -115,14 +157,31 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassParams p) {
     const uint64_t row_base = (high << (n - s0)) + low;  // row of slot t = row_base + (t << L)
     const uint32_t col0 = ct * TILE_COLS;
 
+    // L2 prefetch of the tile that the CTA scheduled `prefetch_dist` blocks later will load: by the time it starts,
+    // its rows are in L2 and the load phase sees L2 latency instead of HBM latency (ncu: long_scoreboard was the top stall)
+    if (p.prefetch_dist && blockIdx.x + p.prefetch_dist < gridDim.x) {
+        const uint32_t fb = blockIdx.x + p.prefetch_dist;
+        const uint32_t fct = fb % col_tiles;
+        const uint64_t frt = fb / col_tiles;
+        const uint64_t frow_base = ((frt >> L) << (n - s0)) + (frt & ((1ull << L) - 1));
+        const int lines_per_row = (TILE_COLS * 4 + 127) / 128;  // 128 B lines per row segment
+        for (int i = tid; i < R * lines_per_row; i += THREADS) {
+            const int t = i / lines_per_row, ln = i % lines_per_row;
+            const uint32_t col = fct * TILE_COLS + ln * 32;
+            if (col < p.width) {
+                const uint32_t* ptr = p.in + (frow_base + ((uint64_t)t << L)) * p.width + col;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
+    }
     for (int i = tid; i < R / 2; i += THREADS) sm_tw[i] = __ldg(p.tw_local + i);
     if (p.pre_lo)
         for (int t = tid; t < R; t += THREADS) sm_row[t] = pow2level(p.pre_lo, p.pre_hi, row_base + ((uint64_t)t << L));
     if (p.pre_lo) __syncthreads();
 
-    // ---- load tile (each row segment is 128 B contiguous)
+    // ---- load tile (each row segment is 2^lc * 4 B contiguous)
     for (int i = tid; i < R * LANES; i += THREADS) {
-        const int t = i / LANES, lane = i % LANES;
+        const int t = i >> ll, lane = i & (LANES - 1);
         const uint32_t col = col0 + lane * VEC;
         Vec<VEC> x;
         if (col < p.width) {
@@ -163,13 +222,19 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassParams p) {
     // ---- K stages: rounds of 3 (radix 8), remainder first
     int u = 0;
     const int rem = K % 3;
-    if (rem == 1) { radix_round<1, VEC>(sm, sm_tw, K, u, tid); u += 1; __syncthreads(); }
-    if (rem == 2) { radix_round<2, VEC>(sm, sm_tw, K, u, tid); u += 2; __syncthreads(); }
-    for (; u < K; u += 3) { radix_round<3, VEC>(sm, sm_tw, K, u, tid); __syncthreads(); }
+#ifndef NTT_NO_TRIVIAL
+    constexpr bool SKIP = true;
+#else
+    constexpr bool SKIP = false;
+#endif
+    if (rem == 1) { if (K == 1) radix_round<1, VEC, SKIP>(sm, sm_tw, K, lc, u, tid); else radix_round<1, VEC, false>(sm, sm_tw, K, lc, u, tid); u += 1; __syncthreads(); }
+    if (rem == 2) { if (K == 2) radix_round<2, VEC, SKIP>(sm, sm_tw, K, lc, u, tid); else radix_round<2, VEC, false>(sm, sm_tw, K, lc, u, tid); u += 2; __syncthreads(); }
+    for (; u + 3 < K; u += 3) { radix_round<3, VEC, false>(sm, sm_tw, K, lc, u, tid); __syncthreads(); }
+    if (u < K) { radix_round<3, VEC, SKIP>(sm, sm_tw, K, lc, u, tid); __syncthreads(); }
 
     // ---- store
     for (int i = tid; i < R * LANES; i += THREADS) {
-        const int t = i / LANES, lane = i % LANES;
+        const int t = i >> ll, lane = i & (LANES - 1);
         const uint32_t col = col0 + lane * VEC;
         if (col >= p.width) continue;
         Vec<VEC> x;
@@ -182,6 +247,175 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassParams p) {
         uint64_t row = row_base + ((uint64_t)t << L);
         if (p.out_natural) row = bb::bitrev((uint32_t)row, n);
         x.store(p.out + row * p.width + col);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA pass: the same K stages, as a persistent warp-specialised kernel.  One producer warp moves whole tiles between
+// HBM and shared memory with cp.async.bulk.tensor (one 4-D box per tile: {columns, low, t, high} of the strided row set)
+// through a 3-stage mbarrier ring; 256 consumer threads only ever touch shared memory, so butterflies of tile c overlap
+// the load of tile c+1 and the store of tile c-1.  Tiles are 2^13 elements (32 KB): 3 stages x 2 CTAs per SM.
+constexpr int TMA_CONSUMERS = 256;
+constexpr int TMA_THREADS = TMA_CONSUMERS + 32;
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_TILE_LOG = 13;
+constexpr int TMA_MAX_K = 8;
+
+struct alignas(64) TensorMap {  // same size/alignment as CUtensorMap (cuda.h), kept opaque here
+    uint64_t opaque[16];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const TensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const TensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 2)
+pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant__ TensorMap out_map, const PassParams p, uint32_t n_tiles) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int K = p.K, n = p.n, s0 = p.s0, lc = p.lc;
+    const int L = n - s0 - K;
+    const int R = 1 << K;
+    const uint32_t tile_bytes = (uint32_t)(R << lc) * 4u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                        // [3] tile landed in smem   (first 128 B: barriers)
+    uint64_t* done = full + TMA_STAGES;                                            // [3] consumers finished the tile
+    uint32_t* bufs = reinterpret_cast<uint32_t*>(smem_raw + 128);                  // TMA_STAGES tiles, each 128-B aligned
+    uint32_t* sm_tw = bufs + TMA_STAGES * (tile_bytes / 4);                        // [R/2] local roots
+    uint32_t* sm_fac = sm_tw + (R > 1 ? R / 2 : 1);                                // [2][R] prescale / twist per row
+    const int tid = threadIdx.x;
+    const uint32_t col_tiles = (p.width + (1u << lc) - 1) >> lc;
+
+    if (tid == 0) {
+        for (int i = 0; i < TMA_STAGES; i++) {
+            mbar_init(full + i, 1);
+            mbar_init(done + i, TMA_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t first = blockIdx.x, stride = gridDim.x;
+    const uint32_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+
+    if (tid >= TMA_CONSUMERS) {
+        // ===== producer warp: one elected lane drives the ring
+        if (tid == TMA_CONSUMERS) {
+            auto coords = [&](uint32_t i, int& c0, int& c1, int& c3) {
+                const uint32_t tile = first + i * stride;
+                const uint32_t ct = tile % col_tiles;
+                const uint64_t rt = tile / col_tiles;
+                c0 = (int)(ct << lc);
+                c1 = (int)(rt & ((1ull << L) - 1));
+                c3 = (int)(rt >> L);
+            };
+            auto load = [&](uint32_t i) {
+                int c0, c1, c3;
+                coords(i, c0, c1, c3);
+                const int b = i % TMA_STAGES;
+                mbar_expect_tx(full + b, tile_bytes);
+                tma_load_4d(bufs + b * (tile_bytes / 4), &in_map, full + b, c0, c1, 0, c3);
+            };
+            for (uint32_t i = 0; i < my_tiles && i < 2; i++) load(i);
+            for (uint32_t c = 0; c < my_tiles; c++) {
+                const int b = c % TMA_STAGES;
+                mbar_wait(done + b, (c / TMA_STAGES) & 1);       // consumers are finished with tile c (they fenced the async proxy)
+                int c0, c1, c3;
+                coords(c, c0, c1, c3);
+                tma_store_4d(&out_map, bufs + b * (tile_bytes / 4), c0, c1, 0, c3);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (c + 2 < my_tiles) {
+                    // buffer (c+2)%3 held tile c-1: its store must have finished reading shared memory
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    load(c + 2);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
+
+    // ===== consumers
+    for (int i = tid; i < R / 2; i += TMA_CONSUMERS) sm_tw[i] = __ldg(p.tw_local + i);
+    const int rem = K % 3;
+    for (uint32_t c = 0; c < my_tiles; c++) {
+        const int b = c % TMA_STAGES;
+        uint32_t* sm = bufs + b * (tile_bytes / 4);
+        const uint32_t tile = first + c * stride;
+        const uint64_t rt = tile / col_tiles;
+        const uint64_t low = rt & ((1ull << L) - 1);
+        const uint64_t high = rt >> L;
+        const uint64_t row_base = (high << (n - s0)) + low;
+        const bool need_twist = L > 0 && low != 0;
+        // per-row factors for this tile (tables are L2/L1 resident); double-buffered by tile parity
+        uint32_t* fac_pre = p.pre_lo ? sm_fac : nullptr;
+        uint32_t* fac_post = need_twist ? sm_fac + R : nullptr;
+        asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");  // previous tile's factors are no longer read
+        for (int t = tid; t < R; t += TMA_CONSUMERS) {
+            if (fac_pre) fac_pre[t] = pow2level(p.pre_lo, p.pre_hi, row_base + ((uint64_t)t << L));
+            if (fac_post) {
+                uint64_t e = (low * (uint64_t)bb::bitrev((uint32_t)t, K)) << s0;
+                if (p.inverse) e = ((1ull << n) - e) & ((1ull << n) - 1);
+                fac_post[t] = pow2level(p.tw_lo, p.tw_hi, e);
+            }
+        }
+        mbar_wait(full + b, (c / TMA_STAGES) & 1);
+        asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");  // factors visible to every consumer
+        int u = 0;
+        const uint32_t* pre = fac_pre;
+        auto post_if_last = [&](int stages) { return (u + stages == K) ? (const uint32_t*)fac_post : (const uint32_t*)nullptr; };
+        if (rem == 1) {
+            if (K == 1) radix_round<1, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(1));
+            else radix_round<1, 4, false, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(1));
+            u += 1; pre = nullptr;
+            asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
+        }
+        if (rem == 2) {
+            if (K == 2) radix_round<2, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(2));
+            else radix_round<2, 4, false, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(2));
+            u += 2; pre = nullptr;
+            asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
+        }
+        for (; u + 3 < K; u += 3) {
+            radix_round<3, 4, false, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, nullptr);
+            pre = nullptr;
+            asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
+        }
+        if (u < K) {
+            radix_round<3, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, fac_post);
+            u += 3;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
+        mbar_arrive(done + b);
     }
 }
 
