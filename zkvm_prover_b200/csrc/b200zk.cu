@@ -326,6 +326,10 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
     }
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e = getenv("B200ZK_L2_FETCH")) {  // experiment knob: L2 fetch granularity hint (32/64/128)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+        cudaGetLastError();
+    }
     {
         cudaDriverEntryPointQueryResult q;
         void* fn = nullptr;
