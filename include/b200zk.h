@@ -115,6 +115,8 @@ int b200zk_lde_commit(b200zk_ctx*, b200zk_mat* const* evals, uint32_t k, uint32_
 /* Mmcs::open_batch(index): rows_out = concatenation over matrices (original order) of row
  * index >> (log2 max_height - log2 height); path_out = depth x 8 siblings, bottom-up */
 int b200zk_merkle_open(b200zk_ctx*, const b200zk_tree*, uint64_t index, uint32_t* h_rows, uint32_t* h_path);
+/* query phase: the same for n_idx indices in one launch + one copy.  h_rows: n_idx x total_width, h_paths: n_idx x depth x 8 */
+int b200zk_merkle_open_many(b200zk_ctx*, const b200zk_tree*, const uint64_t* h_indices, uint32_t n_idx, uint32_t* h_rows, uint32_t* h_paths);
 uint32_t b200zk_tree_depth(const b200zk_tree*);       /* log2 of the tallest height */
 uint32_t b200zk_tree_num_mats(const b200zk_tree*);
 uint64_t b200zk_tree_total_width(const b200zk_tree*); /* sum of widths = elements in h_rows */

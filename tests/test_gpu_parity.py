@@ -113,6 +113,20 @@ def test_merkle_commit_open_verify(z, ctx, shapes):
     assert np.array_equal(mmcs.get_matrices(pd)[0].to_host(), mats[0])
 
 
+def test_open_batch_many_matches_single(z, ctx):
+    mats = [rnd((1 << 12, 24), 1), rnd((1 << 12, 5), 2), rnd((1 << 9, 3), 3)]
+    mmcs = z.MerkleTreeMmcs(ctx)
+    root, pd = mmcs.commit(mats)
+    idxs = [0, 1, 17, 4095, 2048, 1234]
+    many = mmcs.open_batch_many(idxs, pd)
+    for i, (vals, path) in zip(idxs, many):
+        v1, p1 = mmcs.open_batch(i, pd)
+        assert all(np.array_equal(a, b) for a, b in zip(vals, v1)) and np.array_equal(path, p1)
+        mmcs.verify_batch(root, [(m.shape[1], m.shape[0]) for m in mats], i, vals, path)
+    with pytest.raises(z.B200zkError):
+        mmcs.open_batch_many([1 << 12], pd)
+
+
 def test_merkle_fixture_openings_verify_on_device(z, ctx, kats):
     """B-3 / B-3b: openings produced by the real prover verify against its commitments on the device."""
     mmcs = z.MerkleTreeMmcs(ctx)
@@ -261,6 +275,23 @@ def test_commit_phase_matches_oracle(z, ctx, ln, lb, lf):
     assert np.array_equal(res2.commits, oroots) and np.array_equal(res2.final_poly, ofin)
 
 
+def test_commit_phase_final_poly_and_transcript_vs_python_reference(z, ctx):
+    """whole p3-fri commit_phase incl. the final-polynomial iDFT and its observation, against oracle/pyref.py"""
+    from oracle import pyref as R
+    ev = rnd((16, 4), 21)
+    code = O.coset_lde_batch(ev, 1, O.MONTY_ONE, bitrev_out=True)   # 32 EF4, honest codeword of degree < 16
+    seed = rnd(5, 22)
+    c = z.DuplexChallenger(ctx)
+    c.observe(seed)
+    res = z.commit_phase(z.FriConfig(log_blowup=1, log_final_poly_len=2), [code], c, ctx)
+    pc = R.DuplexChallenger()
+    pc.observe_slice(O.from_monty(seed).tolist())
+    commits, _, final_poly, betas = R.fri_commit_phase([O.from_monty(code).tolist()], pc, 2, 4)
+    assert O.from_monty(res.commits).tolist() == commits and O.from_monty(res.betas).tolist() == betas
+    assert O.from_monty(res.final_poly_coeffs).tolist() == final_poly
+    assert O.from_monty(np.array([c.sample()], np.uint32))[0] == pc.sample()  # transcripts stay in lock-step
+
+
 def test_commit_phase_low_degree_and_rollin(z, ctx):
     ev = rnd((512, 4), 9)
     code = O.coset_lde_batch(ev, 1, O.MONTY_ONE, bitrev_out=True)  # 1024 EF4, an honest codeword
@@ -293,6 +324,23 @@ def test_pcs_commit_lde_plus_mmcs(z, ctx):
         assert np.array_equal(pcs.get_evaluations_on_domain(pd, i).to_host(), l)
     rows, path = pcs.mmcs.open_batch(1234, pd)
     pcs.mmcs.verify_batch(root, [(l.shape[1], l.shape[0]) for l in ldes], 1234, rows, path)
+
+
+def test_real_shape_commit_matches_golden(z, ctx):
+    """TwoAdicFriPcs::commit on the REAL shape of the reference's aggregation-layer proof (17 AIRs, heights 2..2^20,
+    widths 1..398, log_blowup 2): root, per-matrix LDE checksums and one opening equal the oracle's golden values
+    (tests/golden/real_shape_commit.json, made by oracle/make_real_shape_golden.py)."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "real_shape_commit.json")))
+    traces = [ctx.alloc(d, w).fill(g["seed_base"] + i) for i, (d, w) in enumerate(zip(g["degrees"], g["widths"]))]
+    pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=g["log_blowup"]), ctx)
+    root, pd = pcs.commit(traces)
+    assert root.tolist() == g["root"]
+    assert [m.checksum() for m in pd.mats] == g["lde_checksums"]
+    rows, path = pcs.mmcs.open_batch(g["index"], pd)
+    assert [r.tolist() for r in rows] == g["opened_rows"] and path.tolist() == g["path"]
+    dims = [(w, d << g["log_blowup"]) for d, w in zip(g["degrees"], g["widths"])]
+    pcs.mmcs.verify_batch(root, dims, g["index"], rows, path)
 
 
 # ------------------------------------------------------------------------------------------ full-size properties

@@ -859,6 +859,34 @@ int b200zk_merkle_open(b200zk_ctx* ctx, const b200zk_tree* t, uint64_t index, ui
     return B200ZK_OK;
 }
 
+int b200zk_merkle_open_many(b200zk_ctx* ctx, const b200zk_tree* t, const uint64_t* h_indices, uint32_t n_idx, uint32_t* h_rows, uint32_t* h_paths) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!t || !h_indices || !h_rows || (!h_paths && t->depth)) return fail(ctx, B200ZK_ERR_ARG, "null tree/output");
+    if (!n_idx) return B200ZK_OK;
+    if (n_idx > 65535) return fail(ctx, B200ZK_ERR_ARG, "at most 65535 indices per call");
+    for (uint32_t i = 0; i < n_idx; i++)
+        if (h_indices[i] >= t->max_h) return fail(ctx, B200ZK_ERR_ARG, "index out of range");
+    CU(cudaSetDevice(ctx->device));
+    const size_t row_words = (size_t)t->total_width * n_idx, path_words = 8ull * t->depth * n_idx;
+    uint32_t* d = nullptr;
+    TRY(dev_alloc(ctx, (row_words + path_words) * 4 + 8ull * n_idx + 16, (void**)&d));
+    uint64_t* d_idx = reinterpret_cast<uint64_t*>(d + ((row_words + path_words + 1) & ~(size_t)1));
+    cudaError_t e = cudaMemcpyAsync(d_idx, h_indices, 8ull * n_idx, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const uint32_t k = (uint32_t)t->mats.size();
+        dim3 grid(std::min<uint32_t>(k, 64), n_idx);
+        mk::open_many_kernel<<<grid, 128, 0, ctx->stream>>>(t->d_open, k, d_idx, n_idx, t->total_width, t->d_digests, t->max_h, t->depth, d, d + row_words);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_rows, d, row_words * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && t->depth) e = cudaMemcpyAsync(h_paths, d + row_words, path_words * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, d);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    return B200ZK_OK;
+}
+
 int b200zk_merkle_verify(b200zk_ctx* ctx, const uint32_t* h_rows, const uint64_t* heights, const uint32_t* widths, uint32_t k, const uint32_t* h_path,
                          uint32_t depth, uint64_t index, const uint32_t h_root[8], int* h_ok) {
     if (!ctx) return B200ZK_ERR_ARG;

@@ -170,6 +170,28 @@ __global__ void open_path_kernel(const uint32_t* __restrict__ digests, uint64_t 
     if (threadIdx.x < 8) path_out[8 * d + threadIdx.x] = digests[8 * (off + sib) + threadIdx.x];
 }
 
+// batched open (query phase): block (q, m) copies row index[q] >> shift of matrix m; path blocks copy the siblings
+__global__ void open_many_kernel(const OpenMat* __restrict__ mats, uint32_t nmats, const uint64_t* __restrict__ indices, uint32_t n_idx, uint64_t total_width,
+                                 const uint32_t* __restrict__ digests, uint64_t max_h, uint32_t depth, uint32_t* __restrict__ rows_out,
+                                 uint32_t* __restrict__ paths_out) {
+    const uint32_t q = blockIdx.y;
+    if (q >= n_idx) return;
+    const uint64_t index = indices[q];
+    for (uint32_t m = blockIdx.x; m < nmats; m += gridDim.x) {
+        OpenMat om = mats[m];
+        const uint32_t* src = om.ptr + (index >> om.shift) * om.width;
+        for (uint32_t c = threadIdx.x; c < om.width; c += blockDim.x) rows_out[q * total_width + om.out_off + c] = src[c];
+    }
+    if (blockIdx.x == 0) {
+        for (uint32_t i = threadIdx.x; i < depth * 8; i += blockDim.x) {
+            const uint32_t d = i >> 3;
+            uint64_t off = 0, n = max_h;
+            for (uint32_t k = 0; k < d; k++) { off += n; n >>= 1; }
+            paths_out[(uint64_t)q * depth * 8 + i] = digests[8 * (off + ((index >> d) ^ 1)) + (i & 7)];
+        }
+    }
+}
+
 // MerkleTreeMmcs::verify_batch, single thread (tiny; device so the host mirror has no CPU hash)
 struct VerifyArgs {
     const uint32_t* rows;       // concatenated opened rows, sorted order (tallest first)

@@ -60,6 +60,7 @@ class CommitPhaseResult:
     data: list               # ProverData per round
     final_poly: np.ndarray   # last folded vector, bit-reversed order (blowup * final_poly_len EF4)
     betas: np.ndarray        # rounds x 4
+    final_poly_coeffs: np.ndarray = None  # p3: reverse_slice_index_bits + idft_algebra, truncated to final_poly_len (EF4 coefficients)
 
 
 def commit_phase(config: FriConfig, inputs, challenger: DuplexChallenger | None, ctx: Context | None = None, betas=None,
@@ -100,6 +101,17 @@ def commit_phase(config: FriConfig, inputs, challenger: DuplexChallenger | None,
         r = rounds.value
         data = [ProverData(ctx, C.c_void_p(trees[i]), []) for i in range(r)] if keep_trees else []
         res = CommitPhaseResult(roots[:r].copy(), data, final, bout[:r].copy())
+        # final polynomial: un-bit-reverse, iDFT every EF4 coefficient column (idft_algebra), keep final_poly_len coefficients,
+        # and let the challenger observe them (p3-fri commit_phase tail)
+        lb = stop.bit_length() - 1
+        nat = final[[int(format(i, f"0{lb}b")[::-1], 2) if lb else 0 for i in range(stop)]]
+        h = C.c_void_p()
+        m = ctx.upload(nat)
+        ctx.check(lib.b200zk_dft_batch(ctx.h, m.h, 0x0FFFFFFE, 1, 0, C.byref(h)))
+        from .device import DeviceMatrix
+        res.final_poly_coeffs = DeviceMatrix(ctx, h, True).to_host()[:config.final_poly_len()]
+        if challenger is not None:
+            challenger.observe(res.final_poly_coeffs.reshape(-1))
         res._input_buffers = owned  # round-0 leaves alias the first input: keep it alive with the result
         owned = []
         return res

@@ -75,6 +75,23 @@ class MerkleTreeMmcs:
             off += m.width
         return out, path
 
+    def open_batch_many(self, indices, prover_data: ProverData):
+        """the query phase's loop over `open_batch` in one launch: -> list of (opened_values, opening_proof)"""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        total = int(self.ctx.lib.b200zk_tree_total_width(prover_data.h))
+        depth = prover_data.depth
+        rows = np.empty((idx.size, total), np.uint32)
+        paths = np.empty((idx.size, depth, DIGEST), np.uint32)
+        self.ctx.check(self.ctx.lib.b200zk_merkle_open_many(self.ctx.h, prover_data.h, idx.ctypes.data, idx.size, rows.ctypes.data, paths.ctypes.data))
+        out = []
+        for q in range(idx.size):
+            vals, off = [], 0
+            for m in prover_data.mats:
+                vals.append(rows[q, off:off + m.width].copy())
+                off += m.width
+            out.append((vals, paths[q]))
+        return out
+
     def get_matrices(self, prover_data: ProverData):
         return list(prover_data.mats)
 
