@@ -263,6 +263,12 @@ def test_commit_phase_matches_oracle(z, ctx, ln, lb, lf):
     res = z.commit_phase(cfg, [vec], c, ctx)
     oroots, obetas, ofin = O.fri_commit_phase(vec, lb, lf, challenger=o)
     assert np.array_equal(res.commits, oroots) and np.array_equal(res.betas, obetas) and np.array_equal(res.final_poly, ofin)
+    # p3-fri tail: un-bit-reverse, idft_algebra, truncate, observe
+    stop = 1 << (lb + lf)
+    nat = ofin[[int(format(i, f"0{lb + lf}b")[::-1], 2) for i in range(stop)]]
+    coeffs = O.dft_batch(nat, inverse=True)[: 1 << lf]
+    assert np.array_equal(res.final_poly_coeffs, coeffs)
+    o.observe(coeffs.reshape(-1))
     assert np.array_equal(c.state(), o.state())
     # per-round trees open and verify (query phase needs them)
     if len(res.data):
