@@ -25,6 +25,44 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     return r;
 }
 
+struct Cursor {
+    int m;
+    uint32_t c, w;
+    const uint32_t* p;
+};
+__device__ __forceinline__ void cursor_next_matrix(const Group& g, uint64_t row, Cursor& cur) {
+    cur.m++;
+    if (cur.m < g.n) {
+        cur.w = g.m[cur.m].width;
+        cur.p = g.m[cur.m].ptr + row * cur.w;
+        cur.c = 0;
+    }
+}
+// next (up to) 8 elements of the concatenated row; returns how many (0 = end of row)
+__device__ __forceinline__ int gather8(const Group& g, uint64_t row, Cursor& cur, uint32_t (&buf)[8]) {
+    if (cur.m >= g.n) return 0;
+    if (cur.w - cur.c >= 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) buf[i] = __ldg(cur.p + cur.c + i);
+        cur.c += 8;
+        if (cur.c == cur.w) cursor_next_matrix(g, row, cur);
+        return 8;
+    }
+    int cnt = 0;
+    while (cnt < 8 && cur.m < g.n) {
+        if (cur.c < cur.w) {
+            const uint32_t x = __ldg(cur.p + cur.c);
+            cur.c++;
+#pragma unroll
+            for (int i = 0; i < 8; i++) buf[i] = (cnt == i) ? x : buf[i];
+            cnt++;
+        } else {
+            cursor_next_matrix(g, row, cur);
+        }
+    }
+    return cnt;
+}
+
 // sponge over the concatenation of row `row` of every matrix of the group -> st[0..8]
 __device__ __forceinline__ void sponge_rows(const Group& g, uint64_t row, uint32_t (&st)[16]) {
 #pragma unroll
@@ -58,21 +96,31 @@ __device__ __forceinline__ void sponge_rows(const Group& g, uint64_t row, uint32
         }
         return;
     }
-    int fill = 0;
-    for (int m = 0; m < g.n; m++) {
-        const uint32_t w = g.m[m].width;
-        const uint32_t* p = g.m[m].ptr + row * w;
-        for (uint32_t c = 0; c < w; c++) {
-            uint32_t x = __ldg(p + c);
+    // general path (ragged widths, several matrices in one sponge -- the shape of real traces): a cursor walks the
+    // concatenated row; 8 elements are gathered with independent loads (selects only where a chunk straddles two
+    // matrices) and the next 8 are already in flight while the permutation runs.
+    Cursor cur;
+    cur.m = 0;
+    cur.c = 0;
+    cur.w = g.m[0].width;
+    cur.p = g.m[0].ptr + row * cur.w;
+    uint32_t buf[8];
+    int cnt = gather8(g, row, cur, buf);
+    while (cnt > 0) {
+        if (cnt == 8) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) st[i] = (fill == i) ? x : st[i];
-            if (++fill == 8) {
-                p2::permute(st);
-                fill = 0;
-            }
+            for (int i = 0; i < 8; i++) st[i] = buf[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) st[i] = (i < cnt) ? buf[i] : st[i];
         }
+        uint32_t nb[8];
+        const int ncnt = gather8(g, row, cur, nb);
+        p2::permute(st);
+#pragma unroll
+        for (int i = 0; i < 8; i++) buf[i] = nb[i];
+        cnt = ncnt;
     }
-    if (fill) p2::permute(st);
 }
 
 __device__ __forceinline__ void store_digest(uint32_t* out, const uint32_t (&st)[16]) {
