@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--log-rows", type=int, default=23)
     ap.add_argument("--width", type=int, default=256)
     ap.add_argument("--added-bits", type=int, default=1)
-    ap.add_argument("--cpu-log-rows", type=int, default=18, help="bounded sample size for the CPU baseline")
+    ap.add_argument("--cpu-log-rows", type=int, default=21, help="bounded sample size for the CPU baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -280,14 +280,11 @@ def main():
     if not args.no_e2e:
         host = torch.empty((n, w), dtype=torch.int32).pin_memory()
         ctx.check(lib.b200zk_mat_download(ctx.h, trace.h, host.data_ptr()))
-        dst = ctx.alloc(n, w)
-
         def step_e2e():
-            ctx.check(lib.b200zk_mat_upload_into(ctx.h, host.data_ptr(), dst.h))
-            dft.coset_lde_batch(dst, b, shift, bit_reversed=True, out=lde)
-            arr = (C.c_void_p * 1)(lde.h)
+            # the C-ABI call a host-side prover makes: host trace in, root out; the library pipelines the PCIe
+            # transfer with the LDE + leaf hashing in column strips (b200zk_lde_commit_host)
             t = C.c_void_p()
-            ctx.check(lib.b200zk_merkle_commit(ctx.h, arr, 1, 0, root.ctypes.data, C.byref(t)))
+            ctx.check(lib.b200zk_lde_commit_host(ctx.h, host.data_ptr(), n, w, b, shift, int(os.environ.get("B200ZK_STRIP", "0")), root.ctypes.data, C.byref(t)))
             lib.b200zk_tree_free(ctx.h, t)
 
         step_e2e()

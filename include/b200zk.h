@@ -112,6 +112,12 @@ int b200zk_merkle_commit(b200zk_ctx*, b200zk_mat* const* mats, uint32_t k, int t
  * inside the tree, commit them; the extended matrices never leave the device. */
 int b200zk_lde_commit(b200zk_ctx*, b200zk_mat* const* evals, uint32_t k, uint32_t added_bits,
                       const uint32_t* shifts_monty, uint32_t h_root[8], b200zk_tree** out);
+/* the same for ONE trace that still lives in host memory (pinned for full speed): the matrix is processed in column
+ * strips so the host->device transfer of strip s+1 overlaps the LDE and leaf hashing of strip s (copy stream + compute
+ * stream).  strip_cols = 0 picks the strip width; small or ragged inputs take the plain upload path.  Bit-identical to
+ * b200zk_mat_upload + b200zk_lde_commit. */
+int b200zk_lde_commit_host(b200zk_ctx*, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits,
+                           uint32_t shift_monty, uint32_t strip_cols, uint32_t h_root[8], b200zk_tree** out);
 /* Mmcs::open_batch(index): rows_out = concatenation over matrices (original order) of row
  * index >> (log2 max_height - log2 height); path_out = depth x 8 siblings, bottom-up */
 int b200zk_merkle_open(b200zk_ctx*, const b200zk_tree*, uint64_t index, uint32_t* h_rows, uint32_t* h_path);

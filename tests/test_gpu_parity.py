@@ -332,6 +332,23 @@ def test_pcs_commit_lde_plus_mmcs(z, ctx):
     pcs.mmcs.verify_batch(root, [(l.shape[1], l.shape[0]) for l in ldes], 1234, rows, path)
 
 
+@pytest.mark.parametrize("n,w,strip", [(14, 256, 0), (14, 256, 32), (16, 64, 16), (15, 96, 0), (10, 256, 0), (14, 40, 0)])
+def test_commit_host_strip_pipeline_matches_plain_commit(z, ctx, n, w, strip):
+    """b200zk_lde_commit_host (column-strip pipeline, H2D overlapped) == upload + lde_commit == oracle"""
+    tr = rnd((1 << n, w), 500 + n + w)
+    pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=1), ctx)
+    r_host, pd_host = pcs.commit_host(tr, strip_cols=strip)
+    r_dev, pd_dev = pcs.commit([tr])
+    assert np.array_equal(r_host, r_dev)
+    assert pd_host.mats[0].checksum() == pd_dev.mats[0].checksum()
+    if n <= 14:
+        lde = O.coset_lde_batch(tr, 1, int(O.to_monty([31])[0]), bitrev_out=True)
+        oroot, _ = O.merkle_commit([lde])
+        assert np.array_equal(r_host, oroot)
+    rows, path = pcs.mmcs.open_batch(77, pd_host)
+    pcs.mmcs.verify_batch(r_host, [(w, 2 << n)], 77, rows, path)
+
+
 def test_real_shape_commit_matches_golden(z, ctx):
     """TwoAdicFriPcs::commit on the REAL shape of the reference's aggregation-layer proof (17 AIRs, heights 2..2^20,
     widths 1..398, log_blowup 2): root, per-matrix LDE checksums and one opening equal the oracle's golden values

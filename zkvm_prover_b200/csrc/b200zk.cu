@@ -40,6 +40,8 @@ struct b200zk_ctx {
     int max_smem_optin = 0;
     int num_sms = 148;
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), null if unavailable
+    cudaStream_t copy_stream = nullptr;  // host->device strip copies of b200zk_lde_commit_host (created on first use)
+    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
 };
 struct b200zk_mat {
     uint32_t* d = nullptr;
@@ -171,10 +173,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 4-D view of the rows a pass touches: {column, low, t, high}; one box = one tile
-int make_pass_map(b200zk_ctx* ctx, const uint32_t* base, uint32_t width, int n, int s0, int K, int lc, ntt::TensorMap* out) {
+int make_pass_map(b200zk_ctx* ctx, const uint32_t* base, uint32_t width, uint32_t pitch, int n, int s0, int K, int lc, ntt::TensorMap* out) {
     const int L = n - s0 - K;
     cuuint64_t dims[4] = {width, 1ull << L, 1ull << K, 1ull << s0};
-    cuuint64_t strides[3] = {(cuuint64_t)width * 4, ((cuuint64_t)width * 4) << L, ((cuuint64_t)width * 4) << (L + K)};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, ((cuuint64_t)pitch * 4) << L, ((cuuint64_t)pitch * 4) << (L + K)};
     cuuint32_t box[4] = {1u << lc, 1, 1u << K, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)base, dims, strides, box,
@@ -201,9 +203,15 @@ struct Scale {
 // n-stage DIF over `rows = 2^n` rows.  src -> dst (first pass), then in place on dst; when out_natural the
 // last pass scatters into dst_final (which must not alias its source).
 int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t* dst_final, int n, uint32_t width, int inverse, Scale pre,
-                  Scale post, int out_natural) {
+                  Scale post, int out_natural, uint32_t src_pitch = 0, uint32_t work_pitch = 0, uint32_t dst_pitch = 0) {
+    if (!src_pitch) src_pitch = width;
+    if (!work_pitch) work_pitch = width;
+    if (!dst_pitch) dst_pitch = width;
     TRY(ensure_roots(ctx, n));
-    const int vec = (width % 4 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)work % 16 == 0) && ((uintptr_t)dst_final % 16 == 0)) ? 4 : 1;
+    const int vec = (width % 4 == 0 && src_pitch % 4 == 0 && work_pitch % 4 == 0 && dst_pitch % 4 == 0 && ((uintptr_t)src % 16 == 0) &&
+                     ((uintptr_t)work % 16 == 0) && ((uintptr_t)dst_final % 16 == 0))
+                        ? 4
+                        : 1;
     const bool tma_ok = vec == 4 && ctx->encode_tiled && tma_enabled();
     std::vector<int> plan = make_plan(n, tma_ok ? ntt::TMA_MAX_K : 0);
     int s0 = 0;
@@ -215,6 +223,8 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         p.in = first ? src : work;
         p.out = last ? dst_final : work;
         p.width = width;
+        p.in_pitch = first ? src_pitch : work_pitch;
+        p.out_pitch = last ? dst_pitch : work_pitch;
         p.n = n;
         p.s0 = s0;
         p.K = K;
@@ -248,8 +258,8 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             const uint64_t tiles = ((1ull << n) >> K) * ((width + tcols - 1) / tcols);
             if (tiles > 0xffffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
             ntt::TensorMap in_map, out_map;
-            TRY(make_pass_map(ctx, p.in, width, n, s0, K, tl, &in_map));
-            TRY(make_pass_map(ctx, p.out, width, n, s0, K, tl, &out_map));
+            TRY(make_pass_map(ctx, p.in, width, p.in_pitch, n, s0, K, tl, &in_map));
+            TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
             const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -363,6 +373,13 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     for (auto& p : ctx->tw_hi) cudaFree(p);
     cudaFree(ctx->tab);
     cudaFree(ctx->d_small);
+    if (ctx->copy_stream) {
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(ctx->ev_copied[i]);
+            cudaEventDestroy(ctx->ev_consumed[i]);
+        }
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -465,6 +482,51 @@ int b200zk_mat_checksum(b200zk_ctx* ctx, const b200zk_mat* m, uint64_t* h_out) {
     return B200ZK_OK;
 }
 
+
+namespace {
+// per-coset scale tables of an LDE: (shift * w'^bitrev(c))^j / N for every coset block c, in ctx->tab
+int lde_tables(b200zk_ctx* ctx, int n, uint32_t added_bits, uint32_t shift) {
+    const uint64_t N = 1ull << n;
+    const uint32_t C = 1u << added_bits;
+    const size_t per = lo_words(N) + hi_words(N);
+    TRY(ensure_tab(ctx, per * C));
+    const uint32_t wprime = bb::two_adic_generator(n + (int)added_bits);
+    const uint32_t ninv = bb::inv(bb::to_monty((uint32_t)(N % bb::P)));
+    for (uint32_t c = 0; c < C; c++) {
+        uint32_t base = bb::mul(shift, bb::pow(wprime, bb::bitrev(c, (int)added_bits)));
+        TRY(pow_tables(ctx, ctx->tab + per * c, ctx->tab + per * c + lo_words(N), base, ninv, N));
+    }
+    return B200ZK_OK;
+}
+
+// coset LDE of `width` columns (n >= 1, bit-reversed rows out); src / dst may be column strips of wider matrices
+// (pitches in elements).  Needs lde_tables() for the same (n, added_bits, shift) to have been enqueued.
+// Work space is the destination itself: block 0 holds the inverse transform in flight, the natural-order coefficients
+// land in the last block, and every coset block is produced from them (the last one in place).
+int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, uint32_t width, uint32_t added_bits, uint32_t* dst, uint32_t dst_pitch) {
+    const uint64_t N = 1ull << n;
+    const uint32_t C = 1u << added_bits;
+    const size_t per = lo_words(N) + hi_words(N);
+    uint32_t* coef = dst + (uint64_t)(C - 1) * N * dst_pitch;
+    b200zk_mat* tmp_inv = nullptr;
+    uint32_t* inv_work = dst;  // block 0
+    uint32_t inv_pitch = dst_pitch;
+    if (C == 1) {  // no spare block: the inverse transform needs its own work area
+        TRY(b200zk_mat_alloc(ctx, N, width, &tmp_inv));
+        inv_work = tmp_inv->d;
+        inv_pitch = width;
+    }
+    int rc = run_transform(ctx, src, inv_work, coef, n, width, /*inverse=*/1, Scale{}, Scale{}, /*out_natural=*/1, src_pitch, inv_pitch, dst_pitch);
+    for (uint32_t c = 0; c < C && rc == B200ZK_OK; c++) {  // the block holding the coefficients goes last (in place)
+        uint32_t* blk = dst + (uint64_t)c * N * dst_pitch;
+        Scale pre{ctx->tab + per * c, ctx->tab + per * c + lo_words(N)};
+        rc = run_transform(ctx, coef, blk, blk, n, width, /*inverse=*/0, pre, Scale{}, 0, dst_pitch, dst_pitch, dst_pitch);
+    }
+    if (tmp_inv) b200zk_mat_free(ctx, tmp_inv);
+    return rc;
+}
+}  // namespace
+
 // ================================================================================================ NTT / LDE
 int b200zk_coset_lde_batch_into(b200zk_ctx* ctx, const b200zk_mat* evals, uint32_t added_bits, uint32_t shift, int bitrev_rows, b200zk_mat* out) {
     TRY(check_mat(ctx, evals));
@@ -491,30 +553,8 @@ int b200zk_coset_lde_batch_into(b200zk_ctx* ctx, const b200zk_mat* evals, uint32
         TRY(b200zk_mat_alloc(ctx, out->rows, W, &tmp_nat));
         final_dst = tmp_nat->d;
     }
-    // coefficients (natural order, unscaled by 1/N) land in the last N-row block of the output;
-    // with added_bits == 0 that block is the whole output, so the inverse transform needs its own work area
-    uint32_t* coef = final_dst + (uint64_t)(C - 1) * N * W;
-    b200zk_mat* tmp_inv = nullptr;
-    uint32_t* inv_work = final_dst;  // block 0
-    if (C == 1) {
-        TRY(b200zk_mat_alloc(ctx, N, W, &tmp_inv));
-        inv_work = tmp_inv->d;
-    }
-    int rc = run_transform(ctx, evals->d, inv_work, coef, n, W, /*inverse=*/1, Scale{}, Scale{}, /*out_natural=*/1);
-    // per-coset scale tables: (shift * w'^bitrev(c))^j / N
-    const size_t per = lo_words(N) + hi_words(N);
-    if (rc == B200ZK_OK) rc = ensure_tab(ctx, per * C);
-    const uint32_t wprime = bb::two_adic_generator(n + (int)added_bits);
-    const uint32_t ninv = bb::inv(bb::to_monty((uint32_t)(N % bb::P)));
-    for (uint32_t c = 0; c < C && rc == B200ZK_OK; c++) {
-        uint32_t base = bb::mul(shift, bb::pow(wprime, bb::bitrev(c, (int)added_bits)));
-        rc = pow_tables(ctx, ctx->tab + per * c, ctx->tab + per * c + lo_words(N), base, ninv, N);
-    }
-    for (uint32_t c = 0; c < C && rc == B200ZK_OK; c++) {  // the block holding the coefficients goes last (in place)
-        uint32_t* dst = final_dst + (uint64_t)c * N * W;
-        Scale pre{ctx->tab + per * c, ctx->tab + per * c + lo_words(N)};
-        rc = run_transform(ctx, coef, dst, dst, n, W, /*inverse=*/0, pre, Scale{}, 0);
-    }
+    int rc = lde_tables(ctx, n, added_bits, shift);
+    if (rc == B200ZK_OK) rc = lde_core(ctx, evals->d, W, n, W, added_bits, final_dst, W);
     if (rc == B200ZK_OK && !bitrev_rows) {
         const int nb = n + (int)added_bits;
         const int vec = (W % 4 == 0) ? 4 : 1;
@@ -524,7 +564,6 @@ int b200zk_coset_lde_batch_into(b200zk_ctx* ctx, const b200zk_mat* evals, uint32
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "bitrev_rows launch failed");
     }
-    if (tmp_inv) b200zk_mat_free(ctx, tmp_inv);
     if (tmp_nat) b200zk_mat_free(ctx, tmp_nat);
     return rc;
 }
@@ -703,8 +742,29 @@ void b200zk_tree_free(b200zk_ctx* ctx, b200zk_tree* t) {
     delete t;
 }
 
+// descriptor array for the open kernels: built on the first open of a tree (a commit never needs it, and staging it
+// from pageable memory would synchronise the stream in the middle of the FRI commit phase)
+static int ensure_open(b200zk_ctx* ctx, b200zk_tree* t) {
+    if (t->d_open) return B200ZK_OK;
+    const uint32_t k = (uint32_t)t->mats.size();
+    TRY(dev_alloc(ctx, sizeof(mk::OpenMat) * k, (void**)&t->d_open));
+    std::vector<mk::OpenMat> om(k);
+    uint64_t off = 0;
+    for (uint32_t i = 0; i < k; i++) {
+        om[i].ptr = t->mats[i]->d;
+        om[i].width = t->mats[i]->width;
+        om[i].shift = t->depth - (uint32_t)log2u(t->mats[i]->rows);
+        om[i].out_off = off;
+        off += t->mats[i]->width;
+    }
+    CU(cudaMemcpyAsync(t->d_open, om.data(), sizeof(mk::OpenMat) * k, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // om is a temporary
+    return B200ZK_OK;
+}
+
 // builds the tree on the stream; the root stays on the device (last digest); no synchronisation
-static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, int take, b200zk_tree** out) {
+typedef int (*LeafFn)(b200zk_ctx*, void* user, uint32_t* d_leaf_digests);
+static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, int take, b200zk_tree** out, LeafFn leaf_fn = nullptr, void* leaf_user = nullptr) {
     *out = nullptr;
     if (!k || !mats) return fail(ctx, B200ZK_ERR_ARG, "no matrices");
     for (uint32_t i = 0; i < k; i++) {
@@ -722,22 +782,7 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
     t->mats.assign(mats, mats + k);
     t->owns_mats = false;  // set at the very end so a failed commit never frees the caller's matrices
     int rc = dev_alloc(ctx, (2 * t->max_h - 1) * 32, (void**)&t->d_digests);
-    if (rc == B200ZK_OK) rc = dev_alloc(ctx, sizeof(mk::OpenMat) * k, (void**)&t->d_open);
-    if (rc == B200ZK_OK) {
-        std::vector<mk::OpenMat> om(k);
-        uint64_t off = 0;
-        for (uint32_t i = 0; i < k; i++) {
-            om[i].ptr = mats[i]->d;
-            om[i].width = mats[i]->width;
-            om[i].shift = t->depth - (uint32_t)log2u(mats[i]->rows);
-            om[i].out_off = off;
-            off += mats[i]->width;
-        }
-        t->total_width = off;
-        cudaError_t e = cudaMemcpyAsync(t->d_open, om.data(), sizeof(mk::OpenMat) * k, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // om is a stack/heap temporary
-        if (e != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
-    }
+    for (uint32_t i = 0; i < k; i++) t->total_width += mats[i]->width;  // open descriptors are built lazily (ensure_open)
     uint64_t off = 0;
     for (uint64_t n = t->max_h; n >= 1; n >>= 1) {
         t->layer_off.push_back(off);
@@ -750,7 +795,9 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
         while (pos < k && mats[order[pos]]->rows == t->max_h) pos++;
         mk::Group g;
         rc = make_group(ctx, mats, order.data() + g0, pos - g0, &g);
-        if (rc == B200ZK_OK) {
+        if (rc == B200ZK_OK && leaf_fn) {
+            rc = leaf_fn(ctx, leaf_user, t->d_digests);  // the caller produces layer 0 itself (strip pipeline)
+        } else if (rc == B200ZK_OK) {
             mk::leaf_hash_kernel<<<(uint32_t)((t->max_h + 255) / 256), 256, 0, ctx->stream>>>(g, t->max_h, t->d_digests);
             ctx->launches++;
             if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "leaf_hash launch failed");
@@ -823,6 +870,98 @@ int b200zk_lde_commit(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uin
     return rc;
 }
 
+
+// ---- TwoAdicFriPcs::commit of ONE host-resident trace with the transfer hidden behind the arithmetic -------------------
+// Everything before tree building is column-local (NTT) or column-sequential (sponge), so the trace is processed in
+// column strips: strip s+1 crosses PCIe on the copy stream while strip s is extended and absorbed on the compute stream.
+namespace {
+struct StripJob {
+    const uint32_t* h_values;
+    uint64_t N;
+    uint32_t W, added_bits, shift, strip;
+    b200zk_mat* lde;
+};
+int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
+    StripJob& j = *static_cast<StripJob*>(user);
+    const int n = log2u(j.N);
+    const uint64_t M = j.N << j.added_bits;
+    if (!ctx->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    uint32_t *sbuf[2] = {nullptr, nullptr}, *cap = nullptr;
+    TRY(dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[0]));
+    TRY(dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[1]));
+    TRY(dev_alloc(ctx, M * 32, (void**)&cap));
+    TRY(lde_tables(ctx, n, j.added_bits, j.shift));
+    // the strip buffers come from the compute stream's pool: the copy stream may only touch them after this point
+    CU(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
+    const uint32_t strips = j.W / j.strip;
+    int rc = B200ZK_OK;
+    for (uint32_t s = 0; s < strips && rc == B200ZK_OK; s++) {
+        const int b = s & 1;
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+        CU(cudaMemcpy2DAsync(sbuf[b], (size_t)j.strip * 4, j.h_values + (size_t)s * j.strip, (size_t)j.W * 4, (size_t)j.strip * 4, j.N, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+        rc = lde_core(ctx, sbuf[b], j.strip, n, j.strip, j.added_bits, j.lde->d + (size_t)s * j.strip, j.W);
+        if (rc != B200ZK_OK) break;
+        CU(cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+        mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, ctx->stream>>>(j.lde->d, j.W, s * j.strip, j.strip, M, cap, s == 0, s + 1 == strips,
+                                                                                           d_digests);
+        LAUNCHED();
+    }
+    dev_free(ctx, sbuf[0]);
+    dev_free(ctx, sbuf[1]);
+    dev_free(ctx, cap);
+    return rc;
+}
+}  // namespace
+
+int b200zk_lde_commit_host(b200zk_ctx* ctx, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits, uint32_t shift, uint32_t strip_cols,
+                           uint32_t h_root[8], b200zk_tree** out) {
+    if (!ctx || !out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    if (!h_values) return fail(ctx, B200ZK_ERR_ARG, "null host pointer");
+    if (!rows || !width || !is_pow2(rows)) return fail(ctx, B200ZK_ERR_SHAPE, "height must be a power of two");
+    const int n = log2u(rows);
+    if (n + (int)added_bits > MAX_LOG) return fail(ctx, B200ZK_ERR_SHAPE, "size exceeds the two-adicity of BabyBear (2^27)");
+    if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t strip = strip_cols ? strip_cols : 64;
+    while (strip > 16 && (width % strip || width / strip < 2)) strip >>= 1;
+    const bool pipelined = n >= 1 && added_bits >= 1 && width % strip == 0 && strip % 16 == 0 && width / strip >= 2 && rows * (uint64_t)width >= (1ull << 22);
+    if (!pipelined) {  // small or ragged: upload, extend, commit
+        b200zk_mat* m = nullptr;
+        TRY(b200zk_mat_upload(ctx, h_values, rows, width, &m));
+        b200zk_mat* arr[1] = {m};
+        int rc = b200zk_lde_commit(ctx, arr, 1, added_bits, &shift, h_root, out);
+        b200zk_mat_free(ctx, m);
+        return rc;
+    }
+    b200zk_mat* lde = nullptr;
+    TRY(b200zk_mat_alloc(ctx, rows << added_bits, width, &lde));
+    StripJob job{h_values, rows, width, added_bits, shift, strip, lde};
+    b200zk_mat* arr[1] = {lde};
+    int rc = commit_async(ctx, arr, 1, /*take=*/1, out, strip_pipeline, &job);
+    if (rc == B200ZK_OK && h_root) rc = b200zk_tree_root(ctx, *out, h_root);
+    else if (rc == B200ZK_OK) rc = b200zk_ctx_sync(ctx);  // h_values must stay valid until the copies are done
+    if (rc != B200ZK_OK) {
+        if (*out) {
+            b200zk_tree_free(ctx, *out);  // frees the LDE with it
+            *out = nullptr;
+        } else {
+            b200zk_mat_free(ctx, lde);
+        }
+    }
+    return rc;
+}
+
 uint32_t b200zk_tree_depth(const b200zk_tree* t) { return t ? t->depth : 0; }
 uint32_t b200zk_tree_num_mats(const b200zk_tree* t) { return t ? (uint32_t)t->mats.size() : 0; }
 uint64_t b200zk_tree_total_width(const b200zk_tree* t) { return t ? t->total_width : 0; }
@@ -840,6 +979,7 @@ int b200zk_merkle_open(b200zk_ctx* ctx, const b200zk_tree* t, uint64_t index, ui
     if (!t || !h_rows || (!h_path && t->depth)) return fail(ctx, B200ZK_ERR_ARG, "null tree/output");
     if (index >= t->max_h) return fail(ctx, B200ZK_ERR_ARG, "index out of range");
     CU(cudaSetDevice(ctx->device));
+    TRY(ensure_open(ctx, const_cast<b200zk_tree*>(t)));
     uint32_t* d = nullptr;
     const size_t words = t->total_width + 8ull * t->depth;
     TRY(dev_alloc(ctx, words * 4, (void**)&d));
@@ -867,6 +1007,7 @@ int b200zk_merkle_open_many(b200zk_ctx* ctx, const b200zk_tree* t, const uint64_
     for (uint32_t i = 0; i < n_idx; i++)
         if (h_indices[i] >= t->max_h) return fail(ctx, B200ZK_ERR_ARG, "index out of range");
     CU(cudaSetDevice(ctx->device));
+    TRY(ensure_open(ctx, const_cast<b200zk_tree*>(t)));
     const size_t row_words = (size_t)t->total_width * n_idx, path_words = 8ull * t->depth * n_idx;
     uint32_t* d = nullptr;
     TRY(dev_alloc(ctx, (row_words + path_words) * 4 + 8ull * n_idx + 16, (void**)&d));
@@ -1083,8 +1224,9 @@ int b200zk_fri_commit_phase(b200zk_ctx* ctx, const uint32_t* const* d_inputs, co
     *h_rounds = max_rounds;
     // scratch: per-round power tables + betas
     size_t tab_per = 4096 + hi_words(len0 / 2);
-    TRY(ensure_tab(ctx, tab_per * std::max<uint32_t>(max_rounds, 1) + 4 * (size_t)max_rounds + 16));
+    TRY(ensure_tab(ctx, tab_per * std::max<uint32_t>(max_rounds, 1) + 12 * (size_t)max_rounds + 32));
     uint32_t* d_betas = ctx->tab + tab_per * std::max<uint32_t>(max_rounds, 1);
+    uint32_t* d_roots = d_betas + 4 * (size_t)max_rounds + 8;  // roots are gathered here: one D2H at the end, no per-round sync
     if (h_betas_forced && max_rounds) CU(cudaMemcpyAsync(d_betas, h_betas_forced, 16ull * max_rounds, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<b200zk_tree*> made;
     const uint32_t* cur = d_inputs[0];
@@ -1109,7 +1251,7 @@ int b200zk_fri_commit_phase(b200zk_ctx* ctx, const uint32_t* const* d_inputs, co
         owned_cur = nullptr;
         made.push_back(t);
         const uint32_t* d_root = t->d_digests + 8 * (2 * t->max_h - 2);
-        cudaError_t e = cudaMemcpyAsync(h_roots + 8 * r, d_root, 32, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(d_roots + 8 * r, d_root, 32, cudaMemcpyDeviceToDevice, ctx->stream);
         if (e != cudaSuccess) { rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e)); break; }
         if (!h_betas_forced) {
             fri::chal_fri_round_kernel<<<1, 32, 0, ctx->stream>>>(chal->d, d_root, d_betas + 4 * r);
@@ -1128,6 +1270,7 @@ int b200zk_fri_commit_phase(b200zk_ctx* ctx, const uint32_t* const* d_inputs, co
     }
     if (rc == B200ZK_OK) {
         cudaError_t e = cudaMemcpyAsync(h_final, cur, len * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && max_rounds) e = cudaMemcpyAsync(h_roots, d_roots, 32ull * max_rounds, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess && h_betas && max_rounds) e = cudaMemcpyAsync(h_betas, d_betas, 16ull * max_rounds, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));

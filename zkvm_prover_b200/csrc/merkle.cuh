@@ -138,6 +138,50 @@ __global__ void __launch_bounds__(256) leaf_hash_kernel(const __grid_constant__ 
     store_digest(digests + 8 * i, st);
 }
 
+// incremental leaf hashing for the column-strip pipeline (b200zk_lde_commit_host): absorbs columns [col0, col0+cols) of
+// every row, cols % 8 == 0.  Between strips only the capacity half of the sponge (st[8..16)) has to be carried: the
+// rate half is overwritten by the next chunk.  `cap` is rows x 8; the last strip writes the digest.
+__global__ void __launch_bounds__(256) leaf_absorb_strip_kernel(const uint32_t* __restrict__ mat, uint32_t pitch, uint32_t col0, uint32_t cols, uint64_t rows,
+                                                                uint32_t* __restrict__ cap, int first, int last, uint32_t* __restrict__ digests) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    uint32_t st[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) st[k] = 0;
+    if (!first) {
+        const uint4* cp = reinterpret_cast<const uint4*>(cap + 8 * i);
+        uint4 a = cp[0], b = cp[1];
+        st[8] = a.x; st[9] = a.y; st[10] = a.z; st[11] = a.w; st[12] = b.x; st[13] = b.y; st[14] = b.z; st[15] = b.w;
+    }
+    const uint4* p = reinterpret_cast<const uint4*>(mat + i * pitch + col0);
+    const uint32_t chunks = cols >> 3;
+    uint4 a = ldg_stream(p), b = ldg_stream(p + 1), c = a, d = b;
+    if (chunks > 1) { c = ldg_stream(p + 2); d = ldg_stream(p + 3); }
+    for (uint32_t k = 0; k < chunks; k += 2) {
+        st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w;
+        st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
+        const uint4 c2 = c, d2 = d;
+        if (k + 2 < chunks) {
+            a = ldg_stream(p + 2 * (k + 2));
+            b = ldg_stream(p + 2 * (k + 2) + 1);
+            if (k + 3 < chunks) { c = ldg_stream(p + 2 * (k + 3)); d = ldg_stream(p + 2 * (k + 3) + 1); }
+        }
+        p2::permute(st);
+        if (k + 1 < chunks) {
+            st[0] = c2.x; st[1] = c2.y; st[2] = c2.z; st[3] = c2.w;
+            st[4] = d2.x; st[5] = d2.y; st[6] = d2.z; st[7] = d2.w;
+            p2::permute(st);
+        }
+    }
+    if (last) {
+        store_digest(digests + 8 * i, st);
+    } else {
+        uint4* cp = reinterpret_cast<uint4*>(cap + 8 * i);
+        cp[0] = make_uint4(st[8], st[9], st[10], st[11]);
+        cp[1] = make_uint4(st[12], st[13], st[14], st[15]);
+    }
+}
+
 __device__ __forceinline__ void compress_node(const uint32_t* __restrict__ prev, uint64_t i, uint32_t (&st)[16]) {
     const uint4* p = reinterpret_cast<const uint4*>(prev + 16 * i);
     uint4 a = p[0], b = p[1], c = p[2], d = p[3];

@@ -31,7 +31,9 @@ constexpr int LO_BITS = 12;  // two-level power tables: x^e = hi[e >> 12] * lo[e
 struct PassParams {
     const uint32_t* in;
     uint32_t* out;
-    uint32_t width;       // columns (row pitch, elements)
+    uint32_t width;       // columns processed
+    uint32_t in_pitch;    // row pitch of `in` in elements (>= width; a column strip of a wider matrix has pitch > width)
+    uint32_t out_pitch;   // row pitch of `out`
     int n;                // log2 of the transform size
     int s0;               // first DIF stage done by this pass
     int K;                // stages in this pass (tile = 2^K rows)
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, NTT_MIN_CTAS) pass_kernel(const PassP
             const int t = i / lines_per_row, ln = i % lines_per_row;
             const uint32_t col = fct * TILE_COLS + ln * 32;
             if (col < p.width) {
-                const uint32_t* ptr = p.in + (frow_base + ((uint64_t)t << L)) * p.width + col;
+                const uint32_t* ptr = p.in + (frow_base + ((uint64_t)t << L)) * p.in_pitch + col;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
             }
         }
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, NTT_MIN_CTAS) pass_kernel(const PassP
         const uint32_t col = col0 + lane * VEC;
         Vec<VEC> x;
         if (col < p.width) {
-            x.load(p.in + (row_base + ((uint64_t)t << L)) * p.width + col);
+            x.load(p.in + (row_base + ((uint64_t)t << L)) * p.in_pitch + col);
             if (p.pre_lo) {
                 const uint32_t f = sm_row[t];
 #pragma unroll
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, NTT_MIN_CTAS) pass_kernel(const PassP
         }
         uint64_t row = row_base + ((uint64_t)t << L);
         if (p.out_natural) row = bb::bitrev((uint32_t)row, n);
-        x.store(p.out + row * p.width + col);
+        x.store(p.out + row * p.out_pitch + col);
     }
 }
 

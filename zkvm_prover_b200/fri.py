@@ -149,5 +149,20 @@ class TwoAdicFriPcs:
         ldes = [DeviceMatrix(self.ctx, C.c_void_p(self.ctx.lib.b200zk_tree_mat(t, i)), False) for i in range(n)]
         return root, ProverData(self.ctx, t, ldes)
 
+    def commit_host(self, trace, strip_cols: int = 0, host_ptr: int | None = None, shape=None):
+        """commit of ONE host-resident trace with the PCIe transfer overlapped with the arithmetic (column-strip
+        pipeline, b200zk_lde_commit_host).  `trace`: C-contiguous uint32 array (pinned memory for full speed), or pass
+        `host_ptr` + `shape` for a raw pinned buffer (e.g. a torch pinned tensor's data_ptr)."""
+        if host_ptr is None:
+            a = np.ascontiguousarray(trace, dtype=np.uint32)
+            host_ptr, shape = a.ctypes.data, a.shape
+        root = np.empty(DIGEST, np.uint32)
+        t = C.c_void_p()
+        self.ctx.check(self.ctx.lib.b200zk_lde_commit_host(self.ctx.h, host_ptr, shape[0], shape[1], self.config.log_blowup, GENERATOR_MONTY, strip_cols,
+                                                           root.ctypes.data, C.byref(t)))
+        n = int(self.ctx.lib.b200zk_tree_num_mats(t))
+        ldes = [DeviceMatrix(self.ctx, C.c_void_p(self.ctx.lib.b200zk_tree_mat(t, i)), False) for i in range(n)]
+        return root, ProverData(self.ctx, t, ldes)
+
     def get_evaluations_on_domain(self, prover_data: ProverData, idx: int) -> DeviceMatrix:
         return prover_data.mats[idx]
