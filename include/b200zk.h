@@ -53,6 +53,8 @@ const char* b200zk_last_error(const b200zk_ctx* ctx);
 int b200zk_ctx_sync(b200zk_ctx* ctx);                  /* wait for the ctx stream */
 void* b200zk_ctx_stream(b200zk_ctx* ctx);              /* the cudaStream_t all work is enqueued on */
 uint64_t b200zk_kernel_launches(const b200zk_ctx* ctx); /* kernels launched so far through this ctx */
+/* device memory freed through this library is kept in a stream-ordered pool for reuse; this returns it to the driver */
+int b200zk_ctx_trim(b200zk_ctx* ctx);
 const char* b200zk_version(void);
 
 /* ---- matrices (p3_matrix::dense::RowMajorMatrix<BabyBear>) ----------------------------------- */

@@ -43,6 +43,7 @@ _SIGS = {
     "b200zk_last_error": (C.c_char_p, [_p]),
     "b200zk_ctx_sync": (_int, [_p]),
     "b200zk_ctx_stream": (_p, [_p]),
+    "b200zk_ctx_trim": (_int, [_p]),
     "b200zk_kernel_launches": (_u64, [_p]),
     "b200zk_mat_alloc": (_int, [_p, _u64, _u32, C.POINTER(_p)]),
     "b200zk_mat_upload": (_int, [_p, _p, _u64, _u32, C.POINTER(_p)]),

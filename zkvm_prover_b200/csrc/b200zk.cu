@@ -389,6 +389,15 @@ int b200zk_ctx_sync(b200zk_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
 }
+int b200zk_ctx_trim(b200zk_ctx* ctx) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return B200ZK_OK;
+}
 void* b200zk_ctx_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t b200zk_kernel_launches(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

@@ -30,6 +30,10 @@ class Context:
     def sync(self):
         self.check(self.lib.b200zk_ctx_sync(self.h))
 
+    def trim(self):
+        """return pooled device memory to the driver"""
+        self.check(self.lib.b200zk_ctx_trim(self.h))
+
     @property
     def stream(self) -> int:
         return self.lib.b200zk_ctx_stream(self.h) or 0
