@@ -87,6 +87,8 @@ class ClockSampler:
 def cpu_sample(log_rows, width, added_bits, steps=1, native=True):
     """oracle port (plain C + OpenMP) on the host cores: LDE + commit of a bounded sample"""
     import numpy as np
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU arm must use all the host threads it can
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import oracle as O
     try:
         if native:

@@ -263,7 +263,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, 2ull * ctx->num_sms);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)NTT_TMA_CTAS * ctx->num_sms);
             ntt::pass_kernel_tma<<<grid, ntt::TMA_THREADS, tsm, ctx->stream>>>(in_map, out_map, p, (uint32_t)tiles);
             LAUNCHED();
             s0 += K;

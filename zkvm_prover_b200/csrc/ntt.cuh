@@ -260,7 +260,13 @@ __global__ void __launch_bounds__(THREADS, NTT_MIN_CTAS) pass_kernel(const PassP
 // the load of tile c+1 and the store of tile c-1.  Tiles are 2^13 elements (32 KB): 3 stages x 2 CTAs per SM.
 constexpr int TMA_CONSUMERS = 256;
 constexpr int TMA_THREADS = TMA_CONSUMERS + 32;
-constexpr int TMA_STAGES = 3;
+#ifndef NTT_TMA_STAGES
+#define NTT_TMA_STAGES 3
+#endif
+#ifndef NTT_TMA_CTAS
+#define NTT_TMA_CTAS 2
+#endif
+constexpr int TMA_STAGES = NTT_TMA_STAGES;
 constexpr int TMA_TILE_LOG = 13;
 constexpr int TMA_MAX_K = 8;
 
@@ -302,7 +308,7 @@ __device__ __forceinline__ void tma_store_4d(const TensorMap* map, const void* s
                  : "memory");
 }
 
-__global__ void __launch_bounds__(TMA_THREADS, 2)
+__global__ void __launch_bounds__(TMA_THREADS, NTT_TMA_CTAS)
 pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant__ TensorMap out_map, const PassParams p, uint32_t n_tiles) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int K = p.K, n = p.n, s0 = p.s0, lc = p.lc;
@@ -347,7 +353,7 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
                 mbar_expect_tx(full + b, tile_bytes);
                 tma_load_4d(bufs + b * (tile_bytes / 4), &in_map, full + b, c0, c1, 0, c3);
             };
-            for (uint32_t i = 0; i < my_tiles && i < 2; i++) load(i);
+            for (uint32_t i = 0; i < my_tiles && i < (uint32_t)(TMA_STAGES - 1); i++) load(i);
             for (uint32_t c = 0; c < my_tiles; c++) {
                 const int b = c % TMA_STAGES;
                 mbar_wait(done + b, (c / TMA_STAGES) & 1);       // consumers are finished with tile c (they fenced the async proxy)
@@ -355,10 +361,12 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
                 coords(c, c0, c1, c3);
                 tma_store_4d(&out_map, bufs + b * (tile_bytes / 4), c0, c1, 0, c3);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (c + 2 < my_tiles) {
-                    // buffer (c+2)%3 held tile c-1: its store must have finished reading shared memory
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    load(c + 2);
+                if (c + (TMA_STAGES - 1) < my_tiles) {
+                    // the buffer of tile c+STAGES-1 last held tile c-1 (3 stages) or tile c itself (2 stages): that store
+                    // must have finished reading shared memory
+                    if (TMA_STAGES >= 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    load(c + (TMA_STAGES - 1));
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
