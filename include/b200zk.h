@@ -171,6 +171,20 @@ int b200zk_fri_commit_phase(b200zk_ctx*, const uint32_t* const* d_inputs, const 
                             const uint32_t* h_betas_forced, uint32_t* h_roots, uint32_t* h_betas,
                             uint32_t* h_final, b200zk_tree** trees, uint32_t* h_rounds);
 
+/* ---- PCS open phase.  Replaces the data-parallel body of p3_fri::TwoAdicFriPcs::open: the LDE stays on
+ *      the device; only opened values (width x EF4) and the per-height reduced-opening vectors' handles cross the ABI --- */
+/* inv_den[i] = 1 / (z - shift * w_M^bitrev(i)), i < 2^log_m  (p3 batch_multiplicative_inverse of the denominators) */
+int b200zk_open_denominators(b200zk_ctx*, uint32_t log_m, uint32_t shift_monty, const uint32_t h_point[4], uint32_t* d_inv_den /* 2^log_m x 4 */);
+/* p3_matrix::Matrix::dot_ext_powers: d_out[r] = sum_c alpha^c * mat[r][c]  (EF4 per row) */
+int b200zk_mat_dot_ext_powers(b200zk_ctx*, const b200zk_mat*, const uint32_t h_alpha[4], uint32_t* d_out /* rows x 4 */);
+/* p3_interpolation::interpolate_coset on the low coset of a bit-reversed LDE (its first rows >> log_blowup rows):
+ * h_ys[c] = p_c(z) for every column.  d_inv_den: b200zk_open_denominators for (log2(rows), shift, z). */
+int b200zk_interpolate_coset(b200zk_ctx*, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift_monty, const uint32_t h_point[4],
+                             const uint32_t* d_inv_den, uint32_t* h_ys /* width x 4 */);
+/* d_ro[i] += alpha_pow_offset * (reduced_ys - d_reduced_row[i]) * d_inv_den[i]   (i < m, EF4 everywhere) */
+int b200zk_reduce_openings(b200zk_ctx*, const uint32_t* d_reduced_row, uint64_t m, const uint32_t* d_inv_den, const uint32_t h_reduced_ys[4],
+                           const uint32_t h_alpha_pow_offset[4], uint32_t* d_ro);
+
 /* ---- raw device memory helpers for FFI users that do not bring their own allocator ------------------ */
 int b200zk_dev_alloc(b200zk_ctx*, uint64_t bytes, void** d_out);
 void b200zk_dev_free(b200zk_ctx*, void* d_ptr);

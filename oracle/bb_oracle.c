@@ -389,6 +389,69 @@ void orc_fri_fold(const u32* in, u64 len, const u32* beta, u32* out) {
     }
 }
 
+/* ------------------------------------------------------------------ PCS open phase primitives
+ * p3_matrix::Matrix::dot_ext_powers(alpha): out[r] = sum_c alpha^c * mat[r][c]   (EF4) */
+static ef4 ef_from_base(u32 x) { ef4 r = {{x, 0, 0, 0}}; return r; }
+static ef4 ef_inv(ef4 a) {
+    /* a^-1 = a^(p^4-2); p^4-2 does not fit 64 bits: use the Frobenius-free route a^(p^4-2) = a^(p-2) * (a^(p(p^3-1)/(p-1))...)
+       -- simpler and obviously right: square-and-multiply over the 124-bit exponent held in two words */
+    unsigned __int128 e = (unsigned __int128)P * P;
+    e = e * P * P - 2; /* p^4 - 2 < 2^124 */
+    ef4 r = ef_from_base(R_MOD_P), b = a;
+    while (e) { if (e & 1) r = ef_mul(r, b); b = ef_mul(b, b); e >>= 1; }
+    return r;
+}
+void orc_ef_inv(const u32* a, u32* out) { orc_init(); ef4 x; memcpy(x.c, a, 16); ef4 r = ef_inv(x); memcpy(out, r.c, 16); }
+void orc_dot_ext_powers(const u32* mat, u64 rows, u64 width, const u32* alpha, u32* out) {
+    orc_init();
+    ef4 a; memcpy(a.c, alpha, 16);
+    ef4* pw = malloc(sizeof(ef4) * (width ? width : 1));
+    pw[0] = ef_from_base(R_MOD_P);
+    for (u64 c = 1; c < width; c++) pw[c] = ef_mul(pw[c - 1], a);
+#pragma omp parallel for schedule(static)
+    for (u64 r = 0; r < rows; r++) {
+        ef4 acc = {{0, 0, 0, 0}};
+        for (u64 c = 0; c < width; c++) acc = ef_add(acc, ef_scale(pw[c], mat[r * width + c]));
+        memcpy(out + 4 * r, acc.c, 16);
+    }
+    free(pw);
+}
+/* p3_interpolation::interpolate_coset(evals on shift*H, shift, point): value of every column's interpolant at the EF4
+ * point z.  `evals` holds the N evaluations in BIT-REVERSED row order (the low coset of a committed LDE).  Definition
+ * level: coefficients by inverse DFT, then Horner at z. */
+void orc_interpolate_coset_bitrev(const u32* evals, u64 n, u64 width, u32 shift, const u32* point, u32* out) {
+    orc_init();
+    u32 lg = 0; while ((1ull << lg) < n) lg++;
+    u32* nat = malloc(4 * n * width);
+    for (u64 i = 0; i < n; i++) memcpy(nat + (u64)bitrev32((u32)i, lg) * width, evals + i * width, 4 * width);
+    orc_dft_batch(nat, n, width, shift, 1, 0); /* coset idft -> coefficients */
+    ef4 z; memcpy(z.c, point, 16);
+    for (u64 c = 0; c < width; c++) {
+        ef4 acc = {{0, 0, 0, 0}};
+        for (u64 j = n; j-- > 0;) acc = ef_add(ef_mul(acc, z), ef_from_base(nat[j * width + c]));
+        memcpy(out + 4 * c, acc.c, 16);
+    }
+    free(nat);
+}
+/* reduced openings of one (matrix, point) pair, p3-fri TwoAdicFriPcs::open:
+ *   ro[i] += alpha_pow_offset * (reduced_ys - reduced_row[i]) / (z - x_i),   x_i = shift * w_M^bitrev(i)
+ * reduced_row = dot_ext_powers(lde, alpha), reduced_ys = sum_c alpha^c * p_c(z). */
+void orc_reduce_openings(const u32* reduced_row, u64 m, u32 shift, const u32* point, const u32* reduced_ys, const u32* alpha_pow_offset, u32* ro) {
+    orc_init();
+    u32 lg = 0; while ((1ull << lg) < m) lg++;
+    u32 w = orc_two_adic_generator(lg);
+    ef4 z, ys, apo; memcpy(z.c, point, 16); memcpy(ys.c, reduced_ys, 16); memcpy(apo.c, alpha_pow_offset, 16);
+#pragma omp parallel for schedule(static)
+    for (u64 i = 0; i < m; i++) {
+        u32 x = bb_mul(shift, bb_pow(w, bitrev32((u32)i, lg)));
+        ef4 den = z; den.c[0] = bb_sub(den.c[0], x);
+        ef4 rr, cur; memcpy(rr.c, reduced_row + 4 * i, 16); memcpy(cur.c, ro + 4 * i, 16);
+        ef4 t = ef_mul(ef_mul(apo, ef_sub(ys, rr)), ef_inv(den));
+        cur = ef_add(cur, t);
+        memcpy(ro + 4 * i, cur.c, 16);
+    }
+}
+
 /* DuplexChallenger<BabyBear, Poseidon2, 16, 8> */
 typedef struct { u32 st[16]; u32 in[8]; u32 nin; u32 out[8]; u32 nout; } orc_chal;
 void orc_chal_init(orc_chal* c) { memset(c, 0, sizeof *c); }

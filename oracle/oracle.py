@@ -47,6 +47,10 @@ def _load(native: bool = False):
         "orc_dft_batch": (None, [_u32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int]),
         "orc_coset_lde_batch": (None, [_u32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _u32p]),
         "orc_fri_fold": (None, [_u32p, C.c_uint64, _u32p, _u32p]),
+        "orc_ef_inv": (None, [_u32p, _u32p]),
+        "orc_dot_ext_powers": (None, [_u32p, C.c_uint64, C.c_uint64, _u32p, _u32p]),
+        "orc_interpolate_coset_bitrev": (None, [_u32p, C.c_uint64, C.c_uint64, C.c_uint32, _u32p, _u32p]),
+        "orc_reduce_openings": (None, [_u32p, C.c_uint64, C.c_uint32, _u32p, _u32p, _u32p, _u32p]),
         "orc_chal_init": (None, [C.c_void_p]), "orc_chal_observe": (None, [C.c_void_p, _u32p, C.c_uint64]),
         "orc_chal_sample": (C.c_uint32, [C.c_void_p]), "orc_chal_sample_ext": (None, [C.c_void_p, _u32p]),
         "orc_chal_sample_bits": (C.c_uint32, [C.c_void_p, C.c_uint32]), "orc_chal_grind": (C.c_uint32, [C.c_void_p, C.c_uint32]),
@@ -194,6 +198,34 @@ def fri_fold(vec, beta):
     out = np.zeros((vec.shape[0] // 2, 4), np.uint32)
     lib().orc_fri_fold(vec, vec.shape[0], np.ascontiguousarray(beta, dtype=np.uint32), out)
     return out
+
+
+def ef_inv(a):
+    out = np.zeros(4, np.uint32)
+    lib().orc_ef_inv(np.ascontiguousarray(a, dtype=np.uint32), out)
+    return out
+
+
+def dot_ext_powers(mat, alpha):
+    mat = np.ascontiguousarray(mat, dtype=np.uint32)
+    out = np.zeros((mat.shape[0], 4), np.uint32)
+    lib().orc_dot_ext_powers(mat, mat.shape[0], mat.shape[1], np.ascontiguousarray(alpha, dtype=np.uint32), out)
+    return out
+
+
+def interpolate_coset_bitrev(evals, shift, point):
+    evals = np.ascontiguousarray(evals, dtype=np.uint32)
+    out = np.zeros((evals.shape[1], 4), np.uint32)
+    lib().orc_interpolate_coset_bitrev(evals, evals.shape[0], evals.shape[1], shift, np.ascontiguousarray(point, dtype=np.uint32), out)
+    return out
+
+
+def reduce_openings(reduced_row, shift, point, reduced_ys, alpha_pow_offset, ro):
+    rr = np.ascontiguousarray(reduced_row, dtype=np.uint32).reshape(-1, 4)
+    ro = np.ascontiguousarray(ro, dtype=np.uint32).reshape(-1, 4).copy()
+    lib().orc_reduce_openings(rr, rr.shape[0], shift, np.ascontiguousarray(point, dtype=np.uint32), np.ascontiguousarray(reduced_ys, dtype=np.uint32),
+                              np.ascontiguousarray(alpha_pow_offset, dtype=np.uint32), ro)
+    return ro
 
 
 class Challenger:

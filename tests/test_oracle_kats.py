@@ -271,3 +271,57 @@ def test_fill_and_checksum_deterministic():
     a = O.fill(1000, 0xB2000000)
     assert a.max() < P and np.array_equal(a[10:20], O.fill(10, 0xB2000000, offset=10))
     assert O.checksum(a) == (O.checksum(a[:500]) + O.checksum(a[500:], offset=500)) & 0xFFFFFFFFFFFFFFFF
+
+
+# ----------------------------------------------------------------------------- PCS open-phase primitives (8(f)-1)
+def test_open_phase_primitives_definitions():
+    """dot_ext_powers / interpolate_coset / reduced openings against their definitions in pure Python."""
+    rng = np.random.default_rng(8)
+    n, w, b = 8, 5, 1
+    tr = rng.integers(0, P, (n, w))
+    alpha = rng.integers(0, P, 4).tolist()
+    z = rng.integers(0, P, 4).tolist()
+    shift_m = int(O.to_monty([31])[0])
+    lde = O.coset_lde_batch(O.to_monty(tr), b, shift_m, bitrev_out=True)          # 2n x w, bit-reversed rows
+    # dot_ext_powers
+    got = O.from_monty(O.dot_ext_powers(lde, O.to_monty(alpha)))
+    pw = [[1, 0, 0, 0]]
+    for _ in range(w - 1):
+        pw.append(R.ef_mul(pw[-1], alpha))
+    ldec = O.from_monty(lde).tolist()
+    exp = []
+    for row in ldec:
+        acc = [0, 0, 0, 0]
+        for c, v in enumerate(row):
+            acc = R.ef_add(acc, R.ef_scale(pw[c], v))
+        exp.append(acc)
+    assert got.tolist() == exp
+    # interpolate_coset on the low coset (first n rows of the bit-reversed LDE = evaluations on 31*H, bit-reversed)
+    ys = O.from_monty(O.interpolate_coset_bitrev(lde[:n], shift_m, O.to_monty(z))).tolist()
+    coeffs = [R.naive_idft(tr[:, c].tolist()) for c in range(w)]                  # p_c in coefficient form (trace domain H)
+    for c in range(w):
+        acc = [0, 0, 0, 0]
+        for coef in reversed(coeffs[c]):
+            acc = R.ef_add(R.ef_mul(acc, z), [coef, 0, 0, 0])
+        assert ys[c] == acc
+    # ef inverse
+    assert R.ef_mul(O.from_monty(O.ef_inv(O.to_monty(z))).tolist(), z) == [1, 0, 0, 0]
+    # reduced openings: (p(z) - p(x)) / (z - x) summed with alpha powers is a polynomial of degree < n-1 in x:
+    rr = O.dot_ext_powers(lde, O.to_monty(alpha))
+    rys = [0, 0, 0, 0]
+    for c in range(w):
+        rys = R.ef_add(rys, R.ef_mul(pw[c], ys[c]))
+    ro = O.reduce_openings(rr, shift_m, O.to_monty(z), O.to_monty(rys), O.to_monty([1, 0, 0, 0]), np.zeros((2 * n, 4), np.uint32))
+    roc = O.from_monty(ro).tolist()
+    m = 2 * n
+    wm = R.two_adic_generator(m.bit_length() - 1)
+    for i in (0, 1, 5, m - 1):
+        x = 31 * pow(wm, R.bitrev(i, m.bit_length() - 1), P) % P
+        den = R.ef_sub(z, [x, 0, 0, 0])
+        assert roc[i] == R.ef_mul(R.ef_sub(rys, exp[i]), R.ef_inv(den))
+    # low-degree check: the quotient's 4 coefficient columns, un-bit-reversed and iDFT'd on the coset, vanish above degree n-2
+    nat = np.zeros((m, 4), np.uint32)
+    for i in range(m):
+        nat[R.bitrev(i, m.bit_length() - 1)] = ro[i]
+    co = O.from_monty(O.dft_batch(nat, shift=shift_m, inverse=True))
+    assert not co[n - 1:].any() and co[: n - 1].any()

@@ -14,7 +14,7 @@ mirror of the Plonky3 trait surface the reference's StarkConfig uses:
 Importing the package needs the built libb200zk.so; using it needs a CUDA device (no CPU fallback).
 """
 from ._lib import B200zkError, load  # noqa: F401
-from .device import Context, DeviceMatrix, default_context  # noqa: F401
+from .device import Context, DeviceBuffer, DeviceMatrix, default_context  # noqa: F401
 from .field import P, MONTY_ONE, to_monty, from_monty, two_adic_generator, GENERATOR_MONTY  # noqa: F401
 from .dft import B200Dft  # noqa: F401
 from .symmetric import Poseidon2BabyBear16, PaddingFreeSponge, TruncatedPermutation  # noqa: F401

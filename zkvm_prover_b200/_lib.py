@@ -90,6 +90,10 @@ _SIGS = {
     "b200zk_fri_commit_layer": (_int, [_p, _p, _u64, _p, C.POINTER(_p)]),
     "b200zk_fri_fold_layer": (_int, [_p, _p, _u64, _p, _p, _p]),
     "b200zk_fri_commit_phase": (_int, [_p, C.POINTER(_p), C.POINTER(_u64), _u32, _u32, _u32, _p, _p, _p, _p, _p, C.POINTER(_p), C.POINTER(_u32)]),
+    "b200zk_open_denominators": (_int, [_p, _u32, _u32, _p, _p]),
+    "b200zk_mat_dot_ext_powers": (_int, [_p, _p, _p, _p]),
+    "b200zk_interpolate_coset": (_int, [_p, _p, _u32, _u32, _p, _p, _p]),
+    "b200zk_reduce_openings": (_int, [_p, _p, _u64, _p, _p, _p, _p]),
     "b200zk_dev_alloc": (_int, [_p, _u64, C.POINTER(_p)]),
     "b200zk_dev_free": (None, [_p, _p]),
     "b200zk_dev_upload": (_int, [_p, _p, _p, _u64]),

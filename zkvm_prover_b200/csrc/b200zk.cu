@@ -16,6 +16,7 @@
 #include "fri.cuh"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "open.cuh"
 
 namespace {
 
@@ -1291,6 +1292,108 @@ int b200zk_fri_commit_phase(b200zk_ctx* ctx, const uint32_t* const* d_inputs, co
         for (auto* t : made) b200zk_tree_free(ctx, t);
     }
     return rc;
+}
+
+
+// ================================================================================================ PCS open phase
+int b200zk_open_denominators(b200zk_ctx* ctx, uint32_t log_m, uint32_t shift, const uint32_t h_point[4], uint32_t* d_inv_den) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!h_point || !d_inv_den) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (log_m > (uint32_t)MAX_LOG) return fail(ctx, B200ZK_ERR_SHAPE, "size exceeds the two-adicity of BabyBear (2^27)");
+    if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
+    CU(cudaSetDevice(ctx->device));
+    TRY(ensure_roots(ctx, (int)log_m));
+    uint32_t* d_z = ctx->d_small + 1024;
+    CU(cudaMemcpyAsync(d_z, h_point, 16, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t threads = ((1ull << log_m) + op::INV_BATCH - 1) / op::INV_BATCH;
+    op::denominators_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, ctx->stream>>>((int)log_m, shift, d_z, ctx->tw_lo[log_m], ctx->tw_hi[log_m], d_inv_den);
+    LAUNCHED();
+    return B200ZK_OK;
+}
+
+int b200zk_mat_dot_ext_powers(b200zk_ctx* ctx, const b200zk_mat* m, const uint32_t h_alpha[4], uint32_t* d_out) {
+    TRY(check_mat(ctx, m));
+    if (!h_alpha || !d_out) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d_alpha = ctx->d_small + 1040;
+    CU(cudaMemcpyAsync(d_alpha, h_alpha, 16, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* d_pw = nullptr;
+    TRY(dev_alloc(ctx, (size_t)m->width * 16, (void**)&d_pw));
+    op::ext_powers_kernel<<<(m->width + 127) / 128, 128, 0, ctx->stream>>>(d_alpha, m->width, d_pw);
+    LAUNCHED();
+    const size_t smem = (size_t)m->width * 16;
+    const bool vec4 = m->width % 4 == 0 && ((uintptr_t)m->d % 16) == 0;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((m->rows + 8 * op::DEP_ROWS - 1) / (8 * op::DEP_ROWS), (uint64_t)ctx->num_sms * 8);
+    if (smem > 48 * 1024) {
+        CU(cudaFuncSetAttribute(op::dot_ext_powers_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(op::dot_ext_powers_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (vec4) op::dot_ext_powers_kernel<4><<<grid, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
+    else op::dot_ext_powers_kernel<1><<<grid, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
+    LAUNCHED();
+    dev_free(ctx, d_pw);
+    return B200ZK_OK;
+}
+
+int b200zk_interpolate_coset(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift, const uint32_t h_point[4], const uint32_t* d_inv_den,
+                             uint32_t* h_ys) {
+    TRY(check_mat(ctx, lde));
+    if (!h_point || !d_inv_den || !h_ys) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (!is_pow2(lde->rows) || (lde->rows >> log_blowup) == 0) return fail(ctx, B200ZK_ERR_SHAPE, "bad LDE height / blow-up");
+    if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
+    CU(cudaSetDevice(ctx->device));
+    const int lm = log2u(lde->rows);
+    const uint64_t n = lde->rows >> log_blowup;
+    const uint32_t W = lde->width;
+    TRY(ensure_roots(ctx, lm));
+    // scale = ((z / shift)^n - 1) / n  in EF4, on the host (a few dozen field operations)
+    bb::ef4 z{{h_point[0], h_point[1], h_point[2], h_point[3]}};
+    bb::ef4 zn = z;
+    for (uint64_t k = 1; k < n; k <<= 1) zn = bb::ef_mul(zn, zn);
+    const uint32_t sn_inv = bb::inv(bb::pow(shift, n));
+    bb::ef4 sc = bb::ef_scale(zn, sn_inv);
+    sc.c[0] = bb::sub(sc.c[0], bb::ONE);
+    sc = bb::ef_scale(sc, bb::inv(bb::to_monty((uint32_t)(n % bb::P))));
+    uint32_t* d_scale = ctx->d_small + 1056;
+    CU(cudaMemcpyAsync(d_scale, sc.c, 16, cudaMemcpyHostToDevice, ctx->stream));
+    const bool vec4 = W % 4 == 0 && ((uintptr_t)lde->d % 16) == 0;
+    const uint32_t cols_per_cta = 256u * (vec4 ? 4 : 1);
+    const uint32_t col_blocks = (W + cols_per_cta - 1) / cols_per_cta;
+    uint32_t row_blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, ((uint64_t)ctx->num_sms * 4 + col_blocks - 1) / col_blocks));
+    const uint32_t rows_per_cta = (uint32_t)(((n + row_blocks - 1) / row_blocks + 63) / 64 * 64);
+    row_blocks = (uint32_t)((n + rows_per_cta - 1) / rows_per_cta);
+    uint32_t *d_partial = nullptr, *d_ys = nullptr;
+    TRY(dev_alloc(ctx, (size_t)row_blocks * W * 16, (void**)&d_partial));
+    TRY(dev_alloc(ctx, (size_t)W * 16, (void**)&d_ys));
+    dim3 grid(row_blocks, col_blocks);
+    if (vec4) op::colwise_bary_kernel<4><<<grid, 256, 0, ctx->stream>>>(lde->d, n, W, lm, shift, ctx->tw_lo[lm], ctx->tw_hi[lm], d_inv_den, rows_per_cta, d_partial);
+    else op::colwise_bary_kernel<1><<<grid, 256, 0, ctx->stream>>>(lde->d, n, W, lm, shift, ctx->tw_lo[lm], ctx->tw_hi[lm], d_inv_den, rows_per_cta, d_partial);
+    LAUNCHED();
+    op::bary_finish_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(d_partial, row_blocks, W, d_scale, d_ys);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(h_ys, d_ys, (size_t)W * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, d_partial);
+    dev_free(ctx, d_ys);
+    return B200ZK_OK;
+}
+
+int b200zk_reduce_openings(b200zk_ctx* ctx, const uint32_t* d_rr, uint64_t m, const uint32_t* d_inv_den, const uint32_t h_rys[4], const uint32_t h_apo[4],
+                           uint32_t* d_ro) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_rr || !d_inv_den || !h_rys || !h_apo || !d_ro) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (!m) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d_c = nullptr;  // the two EF4 constants must outlive this call on the stream: take them from the pool
+    TRY(dev_alloc(ctx, 32, (void**)&d_c));
+    uint32_t tmp[8];
+    memcpy(tmp, h_rys, 16);
+    memcpy(tmp + 4, h_apo, 16);
+    CU(cudaMemcpyAsync(d_c, tmp, 32, cudaMemcpyHostToDevice, ctx->stream));
+    op::reduce_openings_kernel<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(d_rr, m, d_inv_den, d_c, d_c + 4, d_ro);
+    LAUNCHED();
+    dev_free(ctx, d_c);
+    return B200ZK_OK;
 }
 
 // ================================================================================================ raw memory

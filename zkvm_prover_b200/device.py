@@ -88,6 +88,45 @@ def default_context(device: int = 0) -> Context:
     return ctxs[device]
 
 
+class DeviceBuffer:
+    """raw device allocation from the library's pool (EF4 vectors of the open phase, FRI inputs, ...)"""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx, self.nbytes = ctx, nbytes
+        p = C.c_void_p()
+        ctx.check(ctx.lib.b200zk_dev_alloc(ctx.h, nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, ctx: Context, arr) -> "DeviceBuffer":
+        a = np.ascontiguousarray(arr)
+        b = cls(ctx, a.nbytes)
+        ctx.check(ctx.lib.b200zk_dev_upload(ctx.h, b.ptr, a.ctypes.data, a.nbytes))
+        return b
+
+    def zero(self):
+        z = np.zeros(self.nbytes, np.uint8)
+        self.ctx.check(self.ctx.lib.b200zk_dev_upload(self.ctx.h, self.ptr, z.ctypes.data, self.nbytes))
+        return self
+
+    def to_host(self, shape, dtype=np.uint32) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx.check(self.ctx.lib.b200zk_dev_download(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr and self.ctx.h:
+            self.ctx.lib.b200zk_dev_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class DeviceMatrix:
     """RowMajorMatrix<BabyBear> resident in HBM."""
 

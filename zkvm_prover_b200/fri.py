@@ -8,7 +8,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from .challenger import DuplexChallenger
-from .device import Context, DeviceMatrix, default_context
+from .device import Context, DeviceBuffer, DeviceMatrix, default_context
 from .field import GENERATOR_MONTY, P, monty_scalar
 from .mmcs import DIGEST, MerkleTreeMmcs, ProverData
 
@@ -163,6 +163,35 @@ class TwoAdicFriPcs:
         n = int(self.ctx.lib.b200zk_tree_num_mats(t))
         ldes = [DeviceMatrix(self.ctx, C.c_void_p(self.ctx.lib.b200zk_tree_mat(t, i)), False) for i in range(n)]
         return root, ProverData(self.ctx, t, ldes)
+
+    # ---- open phase: the data-parallel body of TwoAdicFriPcs::open, LDEs stay on the device
+    def inv_denominators(self, log_height: int, point) -> DeviceBuffer:
+        """1 / (z - x) for every x of the (bit-reversed) LDE domain GENERATOR * <w_(2^log_height)>"""
+        buf = DeviceBuffer(self.ctx, 16 << log_height)
+        z = np.ascontiguousarray(point, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.b200zk_open_denominators(self.ctx.h, log_height, GENERATOR_MONTY, z.ctypes.data, buf.ptr))
+        return buf
+
+    def dot_ext_powers(self, lde: DeviceMatrix, alpha) -> DeviceBuffer:
+        """Matrix::dot_ext_powers(alpha): one EF4 per LDE row"""
+        buf = DeviceBuffer(self.ctx, 16 * lde.rows)
+        a = np.ascontiguousarray(alpha, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.b200zk_mat_dot_ext_powers(self.ctx.h, lde.h, a.ctypes.data, buf.ptr))
+        return buf
+
+    def interpolate_coset(self, lde: DeviceMatrix, point, inv_den: DeviceBuffer) -> np.ndarray:
+        """opened values p_c(z) of every column (width x 4), from the low coset of the committed LDE"""
+        ys = np.empty((lde.width, 4), np.uint32)
+        z = np.ascontiguousarray(point, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.b200zk_interpolate_coset(self.ctx.h, lde.h, self.config.log_blowup, GENERATOR_MONTY, z.ctypes.data, inv_den.ptr,
+                                                            ys.ctypes.data))
+        return ys
+
+    def reduce_openings(self, reduced_row: DeviceBuffer, m: int, inv_den: DeviceBuffer, reduced_ys, alpha_pow_offset, ro: DeviceBuffer):
+        """ro[i] += alpha^offset * (reduced_ys - reduced_row[i]) / (z - x_i)"""
+        rys = np.ascontiguousarray(reduced_ys, dtype=np.uint32)
+        apo = np.ascontiguousarray(alpha_pow_offset, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.b200zk_reduce_openings(self.ctx.h, reduced_row.ptr, m, inv_den.ptr, rys.ctypes.data, apo.ctypes.data, ro.ptr))
 
     def get_evaluations_on_domain(self, prover_data: ProverData, idx: int) -> DeviceMatrix:
         return prover_data.mats[idx]
