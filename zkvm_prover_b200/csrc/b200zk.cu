@@ -1321,8 +1321,8 @@ int b200zk_mat_dot_ext_powers(b200zk_ctx* ctx, const b200zk_mat* m, const uint32
     TRY(dev_alloc(ctx, (size_t)m->width * 16, (void**)&d_pw));
     op::ext_powers_kernel<<<(m->width + 127) / 128, 128, 0, ctx->stream>>>(d_alpha, m->width, d_pw);
     LAUNCHED();
-    const size_t smem = (size_t)m->width * 16;
     const bool vec4 = m->width % 4 == 0 && ((uintptr_t)m->d % 16) == 0;
+    const size_t smem = (size_t)((m->width + 3) / 4 * 4) * 16;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((m->rows + 8 * op::DEP_ROWS - 1) / (8 * op::DEP_ROWS), (uint64_t)ctx->num_sms * 8);
     if (smem > 48 * 1024) {
         CU(cudaFuncSetAttribute(op::dot_ext_powers_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1357,8 +1357,10 @@ int b200zk_interpolate_coset(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t lo
     uint32_t* d_scale = ctx->d_small + 1056;
     CU(cudaMemcpyAsync(d_scale, sc.c, 16, cudaMemcpyHostToDevice, ctx->stream));
     const bool vec4 = W % 4 == 0 && ((uintptr_t)lde->d % 16) == 0;
-    const uint32_t cols_per_cta = 256u * (vec4 ? 4 : 1);
-    const uint32_t col_blocks = (W + cols_per_cta - 1) / cols_per_cta;
+    const uint32_t vecw = vec4 ? 4 : 1;
+    uint32_t tx_n = 32;  // threads along the columns: enough to cover the width, at most the whole CTA
+    while (tx_n < 256 && tx_n * vecw < W) tx_n <<= 1;
+    const uint32_t col_blocks = (W + tx_n * vecw - 1) / (tx_n * vecw);
     uint32_t row_blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, ((uint64_t)ctx->num_sms * 4 + col_blocks - 1) / col_blocks));
     const uint32_t rows_per_cta = (uint32_t)(((n + row_blocks - 1) / row_blocks + 63) / 64 * 64);
     row_blocks = (uint32_t)((n + rows_per_cta - 1) / rows_per_cta);
@@ -1366,8 +1368,9 @@ int b200zk_interpolate_coset(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t lo
     TRY(dev_alloc(ctx, (size_t)row_blocks * W * 16, (void**)&d_partial));
     TRY(dev_alloc(ctx, (size_t)W * 16, (void**)&d_ys));
     dim3 grid(row_blocks, col_blocks);
-    if (vec4) op::colwise_bary_kernel<4><<<grid, 256, 0, ctx->stream>>>(lde->d, n, W, lm, shift, ctx->tw_lo[lm], ctx->tw_hi[lm], d_inv_den, rows_per_cta, d_partial);
-    else op::colwise_bary_kernel<1><<<grid, 256, 0, ctx->stream>>>(lde->d, n, W, lm, shift, ctx->tw_lo[lm], ctx->tw_hi[lm], d_inv_den, rows_per_cta, d_partial);
+    const size_t rsm = (size_t)256 * vecw * 16;  // [ty][tx * VEC][4] words
+    if (vec4) op::colwise_bary_kernel<4><<<grid, 256, rsm, ctx->stream>>>(lde->d, n, W, lm, shift, ctx->tw_lo[lm], ctx->tw_hi[lm], d_inv_den, rows_per_cta, tx_n, d_partial);
+    else op::colwise_bary_kernel<1><<<grid, 256, rsm, ctx->stream>>>(lde->d, n, W, lm, shift, ctx->tw_lo[lm], ctx->tw_hi[lm], d_inv_den, rows_per_cta, tx_n, d_partial);
     LAUNCHED();
     op::bary_finish_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(d_partial, row_blocks, W, d_scale, d_ys);
     LAUNCHED();

@@ -107,8 +107,14 @@ constexpr int DEP_ROWS = 8;
 template <int VEC>
 __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t* __restrict__ mat, uint64_t rows, uint32_t width, const uint32_t* __restrict__ pw_g,
                                                              uint32_t* __restrict__ out) {
-    extern __shared__ __align__(16) uint32_t pw[];  // width x 4
-    for (uint32_t i = threadIdx.x; i < width * 4; i += blockDim.x) pw[i] = pw_g[i];
+    // powers in shared memory, transposed to [e][column group] so that the 32 lanes of a request read 32 consecutive
+    // 16-byte entries (the natural [column] order made lanes stride by 64 B: a 4-way bank conflict on every read)
+    extern __shared__ __align__(16) uint32_t pw[];  // VEC x ceil(width / VEC) x 4
+    const uint32_t groups = (width + VEC - 1) / VEC;
+    for (uint32_t i = threadIdx.x; i < width; i += blockDim.x) {
+        const uint4 t = *reinterpret_cast<const uint4*>(pw_g + 4 * i);
+        *reinterpret_cast<uint4*>(pw + 4 * ((i % VEC) * groups + i / VEC)) = t;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -116,36 +122,41 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t* __r
     for (uint64_t r0 = warp * DEP_ROWS; r0 < rows; r0 += nwarps * DEP_ROWS) {
         uint32_t part[DEP_ROWS * 4];
 #pragma unroll
-        for (int j = 0; j < DEP_ROWS; j++) {
-            const uint64_t r = r0 + j;
-            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            if (r < rows) {
-                const uint32_t* row = mat + r * width;
-                for (uint32_t c = lane * VEC; c < width; c += 32 * VEC) {
-                    uint32_t v[VEC];
-                    if (VEC == 4) {
-                        const uint4 t = *reinterpret_cast<const uint4*>(row + c);
-                        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
-                    } else {
-                        v[0] = row[c];
-                    }
-                    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int k = 0; k < DEP_ROWS * 4; k++) part[k] = 0;
+        // column block outermost: the 8 rows' loads are issued together (8 independent 16-byte requests per lane in
+        // flight) and the four power entries are read from shared memory once for all 8 rows
+        for (uint32_t c = lane * VEC; c < width; c += 32 * VEC) {
+            uint32_t v[DEP_ROWS][VEC];
 #pragma unroll
-                    for (int e = 0; e < VEC; e++) {
-                        const uint4 p = *reinterpret_cast<const uint4*>(pw + 4 * (c + e));
-                        s0 += (uint64_t)p.x * v[e];
-                        s1 += (uint64_t)p.y * v[e];
-                        s2 += (uint64_t)p.z * v[e];
-                        s3 += (uint64_t)p.w * v[e];
-                        if ((e & 1) || VEC == 1) {  // two products per reduction keep the sum below 2^32 * p
-                            a0 = bb::add(a0, reduce2(s0)); a1 = bb::add(a1, reduce2(s1));
-                            a2 = bb::add(a2, reduce2(s2)); a3 = bb::add(a3, reduce2(s3));
-                            s0 = s1 = s2 = s3 = 0;
-                        }
+            for (int j = 0; j < DEP_ROWS; j++) {
+                const uint64_t r = r0 + j < rows ? r0 + j : rows - 1;  // clamped: the result of a clamped row is discarded
+                const uint32_t* row = mat + r * width + c;
+                if (VEC == 4) {
+                    const uint4 t = *reinterpret_cast<const uint4*>(row);
+                    v[j][0] = t.x; v[j][1 % VEC] = t.y; v[j][2 % VEC] = t.z; v[j][3 % VEC] = t.w;
+                } else {
+                    v[j][0] = row[0];
+                }
+            }
+            uint4 pe[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) pe[e] = *reinterpret_cast<const uint4*>(pw + 4 * (e * groups + c / VEC));
+#pragma unroll
+            for (int j = 0; j < DEP_ROWS; j++) {
+                uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    s0 += (uint64_t)pe[e].x * v[j][e];
+                    s1 += (uint64_t)pe[e].y * v[j][e];
+                    s2 += (uint64_t)pe[e].z * v[j][e];
+                    s3 += (uint64_t)pe[e].w * v[j][e];
+                    if ((e & 1) || VEC == 1) {  // two products per reduction keep the sum below 2^32 * p
+                        part[4 * j] = bb::add(part[4 * j], reduce2(s0)); part[4 * j + 1] = bb::add(part[4 * j + 1], reduce2(s1));
+                        part[4 * j + 2] = bb::add(part[4 * j + 2], reduce2(s2)); part[4 * j + 3] = bb::add(part[4 * j + 3], reduce2(s3));
+                        s0 = s1 = s2 = s3 = 0;
                     }
                 }
             }
-            part[4 * j] = a0; part[4 * j + 1] = a1; part[4 * j + 2] = a2; part[4 * j + 3] = a3;
         }
         // transposed butterfly: after step s every lane keeps half of its values, summed with its partner's copy
         // 32 values -> 16 -> 8 -> 4 -> 2 -> 1; lane l ends with value index l (row l / 4, coefficient l % 4)
@@ -169,19 +180,23 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t* __r
 }
 
 // column-wise barycentric sum over the low coset: acc_c = sum_{i < n} (x_i * inv_den[i]) * M[i][c].
-// Lanes sit on adjacent columns; each CTA owns a slab of rows and writes its partial sums (second kernel reduces).
+// A CTA is TX x TY threads: tx sits on VEC adjacent columns (coalesced rows), ty strides over the rows of the CTA's
+// slab, so narrow matrices still fill the CTA; products of two rows accumulate lazily in 64 bits per reduction.
+// Partial sums of the TY row lanes are combined in shared memory; a second kernel adds the per-CTA partials.
 template <int VEC>
 __global__ void __launch_bounds__(256) colwise_bary_kernel(const uint32_t* __restrict__ mat, uint64_t n, uint32_t width, int lm, uint32_t shift,
                                                            const uint32_t* __restrict__ tw_lo, const uint32_t* __restrict__ tw_hi,
-                                                           const uint32_t* __restrict__ inv_den, uint32_t rows_per_cta, uint32_t* __restrict__ partial) {
-    // thread t handles columns [VEC * t, VEC * t + VEC) of column block blockIdx.y
-    const uint32_t c0 = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+                                                           const uint32_t* __restrict__ inv_den, uint32_t rows_per_cta, uint32_t tx_n, uint32_t* __restrict__ partial) {
+    const uint32_t ty_n = 256 / tx_n;
+    const uint32_t tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+    const uint32_t c0 = (blockIdx.y * tx_n + tx) * VEC;
     const uint64_t r_begin = (uint64_t)blockIdx.x * rows_per_cta;
     const uint64_t r_end = r_begin + rows_per_cta < n ? r_begin + rows_per_cta : n;
     uint32_t acc[VEC][4];
 #pragma unroll
     for (int e = 0; e < VEC; e++) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0;
-    __shared__ uint32_t sd[64 * 4];
+    __shared__ __align__(16) uint32_t sd[64 * 4];
+    extern __shared__ __align__(16) uint32_t red[];  // [ty_n][tx_n * VEC][4] for the final reduction
     for (uint64_t rb = r_begin; rb < r_end; rb += 64) {
         __syncthreads();
         if (threadIdx.x < 64 && rb + threadIdx.x < r_end) {  // d_i = x_i / (z - x_i) for the next 64 rows
@@ -189,37 +204,51 @@ __global__ void __launch_bounds__(256) colwise_bary_kernel(const uint32_t* __res
             const uint32_t e = bb::bitrev((uint32_t)i, lm);
             const uint32_t x = bb::mul(shift, bb::mul(__ldg(tw_lo + (e & 4095)), __ldg(tw_hi + (e >> 12))));
             const ef4 d = bb::ef_scale(ef_load(inv_den + 4 * i), x);
-            sd[4 * threadIdx.x] = d.c[0]; sd[4 * threadIdx.x + 1] = d.c[1]; sd[4 * threadIdx.x + 2] = d.c[2]; sd[4 * threadIdx.x + 3] = d.c[3];
+            ef_store(sd + 4 * threadIdx.x, d);
         }
         __syncthreads();
         if (c0 >= width) continue;
-        const uint64_t lim = r_end - rb < 64 ? r_end - rb : 64;
-        for (uint64_t k = 0; k < lim; k++) {
+        const uint32_t lim = (uint32_t)(r_end - rb < 64 ? r_end - rb : 64);
+        for (uint32_t k = ty; k < lim; k += 2 * ty_n) {  // two rows per reduction
+            const uint32_t k2 = k + ty_n;
+            const bool has2 = k2 < lim;
+            uint32_t v[VEC], u[VEC];
             const uint32_t* row = mat + (rb + k) * width + c0;
-            uint32_t v[VEC];
+            const uint32_t* row2 = mat + (rb + (has2 ? k2 : k)) * width + c0;
             if (VEC == 4) {
                 const uint4 t = *reinterpret_cast<const uint4*>(row);
+                const uint4 t2 = *reinterpret_cast<const uint4*>(row2);
                 v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+                u[0] = t2.x; u[1 % VEC] = t2.y; u[2 % VEC] = t2.z; u[3 % VEC] = t2.w;
             } else {
                 v[0] = row[0];
+                u[0] = row2[0];
             }
-            const uint32_t d0 = sd[4 * k], d1 = sd[4 * k + 1], d2 = sd[4 * k + 2], d3 = sd[4 * k + 3];
+            const uint4 d = *reinterpret_cast<const uint4*>(sd + 4 * k);
+            uint4 g = *reinterpret_cast<const uint4*>(sd + 4 * (has2 ? k2 : k));
+            if (!has2) g = make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int e = 0; e < VEC; e++) {
-                acc[e][0] = bb::add(acc[e][0], bb::mul(d0, v[e]));
-                acc[e][1] = bb::add(acc[e][1], bb::mul(d1, v[e]));
-                acc[e][2] = bb::add(acc[e][2], bb::mul(d2, v[e]));
-                acc[e][3] = bb::add(acc[e][3], bb::mul(d3, v[e]));
+                acc[e][0] = bb::add(acc[e][0], reduce2((uint64_t)d.x * v[e] + (uint64_t)g.x * u[e]));
+                acc[e][1] = bb::add(acc[e][1], reduce2((uint64_t)d.y * v[e] + (uint64_t)g.y * u[e]));
+                acc[e][2] = bb::add(acc[e][2], reduce2((uint64_t)d.z * v[e] + (uint64_t)g.z * u[e]));
+                acc[e][3] = bb::add(acc[e][3], reduce2((uint64_t)d.w * v[e] + (uint64_t)g.w * u[e]));
             }
         }
     }
-    if (c0 < width) {
+    __syncthreads();
 #pragma unroll
-        for (int e = 0; e < VEC; e++)
-            if (c0 + e < width) {
-                uint32_t* o = partial + ((uint64_t)blockIdx.x * width + c0 + e) * 4;
-                o[0] = acc[e][0]; o[1] = acc[e][1]; o[2] = acc[e][2]; o[3] = acc[e][3];
-            }
+    for (int e = 0; e < VEC; e++) {
+        uint32_t* o = red + ((size_t)ty * tx_n * VEC + tx * VEC + e) * 4;
+        o[0] = acc[e][0]; o[1] = acc[e][1]; o[2] = acc[e][2]; o[3] = acc[e][3];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tx_n * VEC * 4; i += 256) {
+        const uint32_t col = blockIdx.y * tx_n * VEC + i / 4;
+        if (col >= width) continue;
+        uint32_t a = 0;
+        for (uint32_t y = 0; y < ty_n; y++) a = bb::add(a, red[(size_t)y * tx_n * VEC * 4 + i]);
+        partial[((uint64_t)blockIdx.x * width + col) * 4 + (i & 3)] = a;
     }
 }
 // ys[c] = scale * sum_b partial[b][c]   (scale = ((z/shift)^n - 1) / n, EF4)
