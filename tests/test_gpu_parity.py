@@ -397,6 +397,51 @@ def test_open_phase_primitives_match_oracle(z, ctx, n, w, b):
     assert np.array_equal(ro.to_host((m, 4)), exp)
 
 
+@pytest.mark.parametrize("lf", [0, 2])
+def test_pcs_open_end_to_end_accepted_by_independent_verifier(z, ctx, lf):
+    """commit -> open (opened values, reduced openings, FRI commit phase, PoW, queries) entirely on the device, then an
+    independent FRI verifier (tests/fri_verifier.py, pure-Python oracle arithmetic) accepts every query."""
+    from oracle import pyref as R
+    import fri_verifier as V
+    lb, nq, pow_bits = 1, 6, 6
+    cfg = z.FriConfig(log_blowup=lb, log_final_poly_len=lf, num_queries=nq, proof_of_work_bits=pow_bits)
+    pcs = z.TwoAdicFriPcs(cfg, ctx)
+    shapes = [[(1 << 9, 12), (1 << 7, 5)], [(1 << 9, 3), (1 << 5, 9)]]           # two commitments, mixed heights
+    traces = [[rnd(sh, 700 + 10 * r + i) for i, sh in enumerate(rs)] for r, rs in enumerate(shapes)]
+    commits = [pcs.commit(ts) for ts in traces]
+    c, pc = z.DuplexChallenger(ctx), R.DuplexChallenger()
+    for root, _ in commits:
+        c.observe(root)
+        pc.observe_slice(O.from_monty(root).tolist())
+    zeta = c.sample_algebra_element()
+    assert O.from_monty(zeta).tolist() == pc.sample_ext()
+    points = []
+    for rs in shapes:
+        per = []
+        for (n, w) in rs:
+            g = z.field.two_adic_generator(n.bit_length() - 1)                     # next-row point zeta * g_trace
+            per.append([zeta, z.field.ef_scale_base(zeta, g)])
+        points.append(per)
+    opened, proof = pcs.open([(pd, pts) for (_, pd), pts in zip(commits, points)], c)
+    # opened values equal the definition (oracle interpolation of the trace at the point)
+    for r, rs in enumerate(shapes):
+        for i, (n, w) in enumerate(rs):
+            lde = O.coset_lde_batch(traces[r][i], lb, z.GENERATOR_MONTY, bitrev_out=True)
+            for k, pt in enumerate(points[r][i]):
+                assert np.array_equal(opened[r][i][k], O.interpolate_coset_bitrev(lde[:n], z.GENERATOR_MONTY, pt))
+    dims = [[(w, n << lb) for (n, w) in rs] for rs in shapes]
+    assert V.verify_pcs_open([root for root, _ in commits], dims, points, opened, proof, pc, lb, lf, pow_bits)
+    # a corrupted opened value must be rejected
+    bad = [[[y.copy() for y in m] for m in rr] for rr in opened]
+    bad[0][0][0][0, 0] ^= 1
+    pc2 = R.DuplexChallenger()
+    for root, _ in commits:
+        pc2.observe_slice(O.from_monty(root).tolist())
+    pc2.sample_ext()
+    with pytest.raises(AssertionError):
+        V.verify_pcs_open([root for root, _ in commits], dims, points, bad, proof, pc2, lb, lf, pow_bits)
+
+
 def test_real_shape_commit_matches_golden(z, ctx):
     """TwoAdicFriPcs::commit on the REAL shape of the reference's aggregation-layer proof (17 AIRs, heights 2..2^20,
     widths 1..398, log_blowup 2): root, per-matrix LDE checksums and one opening equal the oracle's golden values

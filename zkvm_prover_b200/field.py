@@ -36,3 +36,40 @@ def two_adic_generator(bits: int) -> int:
 
 
 GENERATOR_MONTY = monty_scalar(31)  # BabyBear::GENERATOR, the coset shift of trace-domain LDEs
+
+
+# ---- EF4 = F[x]/(x^4 - 11) scalar helpers for host-side glue (a handful of elements per proof; Montgomery u32 in/out)
+def _c(a):
+    return [int(x) * _RINV % P for x in np.asarray(a, dtype=np.uint64).reshape(-1)]
+
+
+def _m(a):
+    return np.array([(x % P) * (1 << 32) % P for x in a], dtype=np.uint32)
+
+
+def ef_mul(a, b):
+    a, b = _c(a), _c(b)
+    t = [0] * 7
+    for i in range(4):
+        for j in range(4):
+            t[i + j] += a[i] * b[j]
+    return _m([t[i] + 11 * (t[i + 4] if i < 3 else 0) for i in range(4)])
+
+
+def ef_add(a, b):
+    return _m([x + y for x, y in zip(_c(a), _c(b))])
+
+
+def ef_scale_base(a, k_canonical: int):
+    return _m([x * k_canonical for x in _c(a)])
+
+
+def ef_pow(a, e: int):
+    r = _m([1, 0, 0, 0])
+    b = np.asarray(a, dtype=np.uint32)
+    while e:
+        if e & 1:
+            r = ef_mul(r, b)
+        b = ef_mul(b, b)
+        e >>= 1
+    return r

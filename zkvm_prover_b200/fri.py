@@ -9,7 +9,7 @@ import numpy as np
 
 from .challenger import DuplexChallenger
 from .device import Context, DeviceBuffer, DeviceMatrix, default_context
-from .field import GENERATOR_MONTY, P, monty_scalar
+from .field import GENERATOR_MONTY, P, ef_add, ef_mul, ef_pow, ef_scale_base, monty_scalar, two_adic_generator
 from .mmcs import DIGEST, MerkleTreeMmcs, ProverData
 
 
@@ -99,7 +99,8 @@ def commit_phase(config: FriConfig, inputs, challenger: DuplexChallenger | None,
             config.log_final_poly_len, challenger.h if challenger is not None else None, bf.ctypes.data if bf is not None else None,
             roots.ctypes.data, bout.ctypes.data, final.ctypes.data, trees if keep_trees else None, C.byref(rounds)))
         r = rounds.value
-        data = [ProverData(ctx, C.c_void_p(trees[i]), []) for i in range(r)] if keep_trees else []
+        data = [ProverData(ctx, C.c_void_p(trees[i]), [DeviceMatrix(ctx, C.c_void_p(lib.b200zk_tree_mat(C.c_void_p(trees[i]), 0)), False)])
+                for i in range(r)] if keep_trees else []
         res = CommitPhaseResult(roots[:r].copy(), data, final, bout[:r].copy())
         # final polynomial: un-bit-reverse, iDFT every EF4 coefficient column (idft_algebra), keep final_poly_len coefficients,
         # and let the challenger observe them (p3-fri commit_phase tail)
@@ -108,7 +109,6 @@ def commit_phase(config: FriConfig, inputs, challenger: DuplexChallenger | None,
         h = C.c_void_p()
         m = ctx.upload(nat)
         ctx.check(lib.b200zk_dft_batch(ctx.h, m.h, 0x0FFFFFFE, 1, 0, C.byref(h)))
-        from .device import DeviceMatrix
         res.final_poly_coeffs = DeviceMatrix(ctx, h, True).to_host()[:config.final_poly_len()]
         if challenger is not None:
             challenger.observe(res.final_poly_coeffs.reshape(-1))
@@ -192,6 +192,65 @@ class TwoAdicFriPcs:
         rys = np.ascontiguousarray(reduced_ys, dtype=np.uint32)
         apo = np.ascontiguousarray(alpha_pow_offset, dtype=np.uint32)
         self.ctx.check(self.ctx.lib.b200zk_reduce_openings(self.ctx.h, reduced_row.ptr, m, inv_den.ptr, rys.ctypes.data, apo.ctypes.data, ro.ptr))
+
+    def open(self, rounds, challenger: DuplexChallenger):
+        """The prover side of p3_fri::TwoAdicFriPcs::open, with every data-parallel step on the device.
+
+        rounds: list of (ProverData, points) where points[i] is the list of EF4 opening points of matrix i of that
+        commitment (e.g. [zeta, zeta * g_trace]).  Returns (opened_values, proof):
+          opened_values[round][matrix][point] = (width, 4) array of p_c(z)
+          proof = {commit_phase_commits, final_poly, pow_witness, query_indices, input_openings, commit_phase_openings}
+        Composition (alpha sampled first, per-height reduced openings with running alpha offsets, inputs rolled into
+        the FRI folding at their height, PoW, then queries) follows p3-fri as of the reference's fixture era; the order
+        of transcript operations is restated from memory of that crate and is NOT pinned by a reference vector
+         -- the arithmetic of every step is."""
+        alpha = challenger.sample_algebra_element()
+        reduced, num_reduced, opened, keep = {}, {}, [], []
+        for pd, points in rounds:
+            per_round = []
+            for lde, pts in zip(pd.mats, points):
+                lh = lde.rows.bit_length() - 1
+                if lh not in reduced:
+                    reduced[lh] = DeviceBuffer(self.ctx, 16 * lde.rows).zero()
+                    num_reduced[lh] = 0
+                rr = self.dot_ext_powers(lde, alpha)
+                per_mat = []
+                for zpt in pts:
+                    inv = self.inv_denominators(lh, zpt)
+                    ys = self.interpolate_coset(lde, zpt, inv)
+                    rys = np.zeros(4, np.uint32)
+                    apw = np.array([monty_scalar(1), 0, 0, 0], np.uint32)
+                    for c in range(lde.width):
+                        rys = ef_add(rys, ef_mul(apw, ys[c]))
+                        apw = ef_mul(apw, alpha)
+                    apo = ef_pow(alpha, num_reduced[lh])
+                    self.reduce_openings(rr, lde.rows, inv, rys, apo, reduced[lh])
+                    num_reduced[lh] += lde.width
+                    per_mat.append(ys)
+                    keep.append(inv)
+                keep.append(rr)
+                per_round.append(per_mat)
+            opened.append(per_round)
+        heights = sorted(reduced, reverse=True)
+        inputs = [(reduced[lh].ptr, 1 << lh) for lh in heights]
+        res = commit_phase(self.config, inputs, challenger, self.ctx)
+        pow_witness = challenger.grind(self.config.proof_of_work_bits)
+        log_max = heights[0]
+        indices = [challenger.sample_bits(log_max) for _ in range(self.config.num_queries)]
+        input_openings = []
+        for pd, _ in rounds:
+            lmh = max(m.rows for m in pd.mats).bit_length() - 1
+            input_openings.append(self.mmcs.open_batch_many([i >> (log_max - lmh) for i in indices], pd))
+        cp_openings = []
+        for r, tree in enumerate(res.data):
+            opens = self.mmcs.open_batch_many([(i >> r) >> 1 for i in indices], tree)
+            cp_openings.append([(vals[0].reshape(2, 4), path) for vals, path in opens])
+        proof = {"alpha": alpha, "commit_phase_commits": res.commits, "betas": res.betas, "final_poly": res.final_poly_coeffs,
+                 "pow_witness": pow_witness, "query_indices": indices, "input_openings": input_openings, "commit_phase_openings": cp_openings,
+                 "log_max_height": log_max}
+        res._keep = (reduced, keep)
+        proof["_commit_phase"] = res
+        return opened, proof
 
     def get_evaluations_on_domain(self, prover_data: ProverData, idx: int) -> DeviceMatrix:
         return prover_data.mats[idx]
