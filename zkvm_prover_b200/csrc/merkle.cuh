@@ -19,10 +19,20 @@ struct Group {
     int fast8;  // every matrix: width % 8 == 0 and 32-byte aligned base  -> vector path
 };
 
+// row data is read through L1 (allocating): a thread consumes its 128-byte line in two 64-byte steps ~100 us apart, and
+// the per-SM working set (resident threads x 128 B <= 160 KB) fits the L1, so the second half never goes back to L2/HBM
+// (with L1::no_allocate the kernel moved 26.6 GB for 17.7 GB of data)
+#ifndef MK_LDG_NOALLOC
+#define MK_LDG_NOALLOC 0
+#endif
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+#if MK_LDG_NOALLOC
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+#else
+    return __ldg(p);
+#endif
 }
 
 struct Cursor {
