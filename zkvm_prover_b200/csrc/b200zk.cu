@@ -32,7 +32,7 @@ struct b200zk_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
-    uint32_t* tw_local[2][KMAX_BIG + 1] = {};
+    uint2* tw_local[2][KMAX_BIG + 1] = {};  // Shoup pairs
     uint32_t* tw_lo[MAX_LOG + 1] = {};
     uint32_t* tw_hi[MAX_LOG + 1] = {};
     uint32_t* tab = nullptr;  // scratch for per-call power tables (stream ordered reuse)
@@ -148,11 +148,10 @@ int ensure_roots(b200zk_ctx* ctx, int n) {
 int ensure_local(b200zk_ctx* ctx, int inverse, int K) {
     if (ctx->tw_local[inverse][K]) return B200ZK_OK;
     uint32_t half = K ? (1u << (K - 1)) : 1;
-    TRY(dev_alloc(ctx, std::max<uint32_t>(half, 4096u + 1) * 4, (void**)&ctx->tw_local[inverse][K]));
+    TRY(dev_alloc(ctx, (size_t)half * 8, (void**)&ctx->tw_local[inverse][K]));
     uint32_t g = bb::two_adic_generator(K);
     if (inverse) g = bb::inv(g);
-    // reuse the two-level generator with every entry in `lo` (half <= 512 < 4096); hi gets one dummy entry
-    ntt::pow_table_kernel<<<(half + 255) / 256, 256, 0, ctx->stream>>>(ctx->tw_local[inverse][K], ctx->tw_local[inverse][K] + 4096, g, bb::ONE, half, 1);
+    ntt::shoup_table_kernel<<<(half + 255) / 256, 256, 0, ctx->stream>>>(ctx->tw_local[inverse][K], g, half);
     LAUNCHED();
     return B200ZK_OK;
 }
@@ -261,7 +260,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             ntt::TensorMap in_map, out_map;
             TRY(make_pass_map(ctx, p.in, width, p.in_pitch, n, s0, K, tl, &in_map));
             TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
-            const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
+            const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (2 * std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)NTT_TMA_CTAS * ctx->num_sms);
@@ -270,7 +269,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             s0 += K;
             continue;
         }
-        const size_t smem = (R * tile_cols + std::max<uint64_t>(R / 2, 1) + R) * 4;
+        const size_t smem = (R * tile_cols + 2 * std::max<uint64_t>(R / 2, 1) + R) * 4;
         const uint64_t blocks = ((1ull << n) >> K) * col_tiles;
         if (blocks > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
         if (vec == 4) {
