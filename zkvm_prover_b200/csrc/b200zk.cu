@@ -306,6 +306,16 @@ __global__ void checksum_kernel(const uint32_t* __restrict__ v, uint64_t n, unsi
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
+// dst[r][c] = c < width ? src[r][c] : 0 for c < dst_width (re-pitching: pad an odd-width matrix to a multiple of 4
+// columns so it can take the vectorised / TMA NTT path, and compact the result again)
+__global__ void repitch_kernel(const uint32_t* __restrict__ src, uint32_t src_pitch, uint32_t width, uint32_t* __restrict__ dst, uint32_t dst_pitch,
+                               uint32_t dst_width, uint64_t rows) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * dst_width) return;
+    const uint64_t r = i / dst_width;
+    const uint32_t col = (uint32_t)(i % dst_width);
+    dst[r * dst_pitch + col] = col < width ? src[r * src_pitch + col] : 0u;
+}
 __global__ void replicate_row_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t rows, uint32_t width) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * width) out[i] = in[i % width];
@@ -563,7 +573,29 @@ int b200zk_coset_lde_batch_into(b200zk_ctx* ctx, const b200zk_mat* evals, uint32
         final_dst = tmp_nat->d;
     }
     int rc = lde_tables(ctx, n, added_bits, shift);
-    if (rc == B200ZK_OK) rc = lde_core(ctx, evals->d, W, n, W, added_bits, final_dst, W);
+    if (rc == B200ZK_OK && W % 4 != 0 && N * W >= (1ull << 14)) {
+        // ragged width (the usual case for real traces): extend a zero-padded copy whose pitch is a multiple of 4 so the
+        // passes run vectorised through TMA, then compact the result (two extra streaming copies, ~2.5x faster overall)
+        const uint32_t Wp = (W + 3) & ~3u;
+        const uint64_t M = N << added_bits;
+        uint32_t *pin = nullptr, *pout = nullptr;
+        rc = dev_alloc(ctx, N * Wp * 4, (void**)&pin);
+        if (rc == B200ZK_OK) rc = dev_alloc(ctx, M * Wp * 4, (void**)&pout);
+        if (rc == B200ZK_OK) {
+            repitch_kernel<<<(uint32_t)((N * Wp + 255) / 256), 256, 0, ctx->stream>>>(evals->d, W, W, pin, Wp, Wp, N);
+            ctx->launches++;
+            rc = lde_core(ctx, pin, Wp, n, Wp, added_bits, pout, Wp);
+        }
+        if (rc == B200ZK_OK) {
+            repitch_kernel<<<(uint32_t)((M * W + 255) / 256), 256, 0, ctx->stream>>>(pout, Wp, W, final_dst, W, W, M);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "repitch launch failed");
+        }
+        dev_free(ctx, pin);
+        dev_free(ctx, pout);
+    } else if (rc == B200ZK_OK) {
+        rc = lde_core(ctx, evals->d, W, n, W, added_bits, final_dst, W);
+    }
     if (rc == B200ZK_OK && !bitrev_rows) {
         const int nb = n + (int)added_bits;
         const int vec = (W % 4 == 0) ? 4 : 1;
