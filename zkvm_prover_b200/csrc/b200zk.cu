@@ -186,6 +186,19 @@ int make_pass_map(b200zk_ctx* ctx, const uint32_t* base, uint32_t width, uint32_
     return B200ZK_OK;
 }
 
+// destination of a scatter pass: natural-order rows k1 * 2^(n-K) + q as the box {column, q, k1}
+int make_natural_map(b200zk_ctx* ctx, const uint32_t* base, uint32_t width, uint32_t pitch, int n, int K, int lc, ntt::TensorMap* out) {
+    cuuint64_t dims[4] = {width, 1ull << (n - K), 1ull << K, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, ((cuuint64_t)pitch * 4) << (n - K), ((cuuint64_t)pitch * 4) << n};
+    cuuint32_t box[4] = {1u << lc, 1, 1u << K, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)base, dims, strides, box,
+                                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, B200ZK_ERR_CUDA, "cuTensorMapEncodeTiled (natural) failed: " + std::to_string((int)r));
+    return B200ZK_OK;
+}
+
 bool tma_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -249,7 +262,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             p.prefetch_dist = e ? (uint32_t)atoi(e) : 148u; // measured best look-ahead (profiles/ntt_tuning_r01.txt)
         }
         const uint64_t R = 1ull << K;
-        if (tma_ok && K <= ntt::TMA_MAX_K && !p.out_natural && !p.post_lo) {
+        if (tma_ok && K <= ntt::TMA_MAX_K && !p.post_lo) {
             // persistent warp-specialised TMA pass: 2^13-element tiles, 3-stage ring, 2 CTAs per SM
             int tl = std::min(ntt::TMA_TILE_LOG - K, ntt::MAX_TILE_COLS_LOG);
             while (tl > 2 && (1u << (tl - 1)) >= width) tl--;
@@ -259,7 +272,8 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             if (tiles > 0xffffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
             ntt::TensorMap in_map, out_map;
             TRY(make_pass_map(ctx, p.in, width, p.in_pitch, n, s0, K, tl, &in_map));
-            TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
+            if (p.out_natural) TRY(make_natural_map(ctx, p.out, width, p.out_pitch, n, K, tl, &out_map));
+            else TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
             const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (2 * std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
             CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));

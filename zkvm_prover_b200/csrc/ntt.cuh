@@ -74,7 +74,9 @@ __device__ __forceinline__ uint32_t pow2level(const uint32_t* lo, const uint32_t
 // LAST: this round ends the tile's DIF (lowbits == 0), so the twiddle index of a butterfly depends only on q and the
 // butterflies with (q & (half-1)) == 0 multiply by w^0 = 1: they are done as plain subtractions (7 of the 12 butterflies
 // of a radix-8 round).
-template <int k, int VEC, bool LAST, int NT = THREADS>
+// BREV_OUT (final round of a scatter pass, TMA kernel only): row t' is written to slot bitrev_K(t') so the tile leaves in
+// natural coefficient order; every thread has exactly one group then, and a named barrier separates loads from stores.
+template <int k, int VEC, bool LAST, int NT = THREADS, bool BREV_OUT = false>
 __device__ __forceinline__ void radix_round(uint32_t* sm, const uint2* sm_tw, int K, int lc, int u, int tid, const uint32_t* fac_pre = nullptr,
                                             const uint32_t* fac_post = nullptr) {
     constexpr int LV = VEC == 4 ? 2 : 0;
@@ -137,9 +139,18 @@ __device__ __forceinline__ void radix_round(uint32_t* sm, const uint2* sm_tw, in
                 for (int c = 0; c < VEC; c++) x[q].v[c] = bb::mul(x[q].v[c], f);
             }
         }
+        if (BREV_OUT) {
+            // all loads of the round are done before any permuted store; the non-.aligned form because a narrow tile leaves
+            // part of a warp without a group (those lanes arrive from the statement after the loop)
+            asm volatile("barrier.sync 1, %0;" ::"n"(NT) : "memory");
 #pragma unroll
-        for (int q = 0; q < R; q++) x[q].store(sm + (base + (q << lowbits)) * TILE_COLS + lane * VEC);
+            for (int q = 0; q < R; q++) x[q].store(sm + bb::bitrev((uint32_t)(base + (q << lowbits)), K) * TILE_COLS + lane * VEC);
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; q++) x[q].store(sm + (base + (q << lowbits)) * TILE_COLS + lane * VEC);
+        }
     }
+    if (BREV_OUT && tid >= groups) asm volatile("barrier.sync 1, %0;" ::"n"(NT) : "memory");  // idle threads still join the barrier
 }
 
 template <int VEC>
@@ -364,6 +375,10 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
                 mbar_wait(done + b, (c / TMA_STAGES) & 1);       // consumers are finished with tile c (they fenced the async proxy)
                 int c0, c1, c3;
                 coords(c, c0, c1, c3);
+                if (p.out_natural) {  // last pass (L = 0): the tile leaves as rows k1 * 2^(n-K) + bitrev(high), k1 = 0..2^K-1
+                    c1 = (int)bb::bitrev((uint32_t)c3, n - K);
+                    c3 = 0;
+                }
                 tma_store_4d(&out_map, bufs + b * (tile_bytes / 4), c0, c1, 0, c3);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 if (c + (TMA_STAGES - 1) < my_tiles) {
@@ -408,14 +423,17 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
         int u = 0;
         const uint32_t* pre = fac_pre;
         auto post_if_last = [&](int stages) { return (u + stages == K) ? (const uint32_t*)fac_post : (const uint32_t*)nullptr; };
+        const bool brev = p.out_natural != 0;
         if (rem == 1) {
-            if (K == 1) radix_round<1, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(1));
+            if (K == 1 && brev) radix_round<1, 4, true, TMA_CONSUMERS, true>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(1));
+            else if (K == 1) radix_round<1, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(1));
             else radix_round<1, 4, false, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(1));
             u += 1; pre = nullptr;
             asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
         }
         if (rem == 2) {
-            if (K == 2) radix_round<2, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(2));
+            if (K == 2 && brev) radix_round<2, 4, true, TMA_CONSUMERS, true>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(2));
+            else if (K == 2) radix_round<2, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(2));
             else radix_round<2, 4, false, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(2));
             u += 2; pre = nullptr;
             asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
@@ -426,7 +444,8 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
             asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
         }
         if (u < K) {
-            radix_round<3, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, fac_post);
+            if (brev) radix_round<3, 4, true, TMA_CONSUMERS, true>(sm, sm_tw, K, lc, u, tid, pre, fac_post);
+            else radix_round<3, 4, true, TMA_CONSUMERS>(sm, sm_tw, K, lc, u, tid, pre, fac_post);
             u += 3;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
