@@ -524,3 +524,48 @@ def test_max_baseline_rows_lde_commit_properties(z, ctx):
     assert np.array_equal(root2, root) and pd2.mats[0].checksum() == cs
     pd2.free()
     ctx.trim()
+
+
+# ------------------------------------------------------------------------------------------ re-entrancy
+def test_concurrent_contexts_from_host_threads(z):
+    """the Plonky3 objects are Clone + Sync and are called from rayon worker threads, so the
+    library must be re-entrant: one ctx per thread, no hidden shared mutable state.  Four threads run the whole path
+    (LDE + commit + openings) at once, each on its own context and input, and every result must equal the oracle's."""
+    import threading
+
+    shapes = [(1 << 10, 24), (1 << 12, 8), (1 << 9, 40), (1 << 11, 16)]
+    inputs = [rnd(s, 900 + i) for i, s in enumerate(shapes)]
+    expect = []
+    for m in inputs:
+        lde = O.coset_lde_batch(m, 1, int(O.to_monty([31])[0]), bitrev_out=True)
+        root, layers = O.merkle_commit([lde])
+        expect.append((lde, root))
+    results = [None] * len(inputs)
+    errors = []
+    barrier = threading.Barrier(len(inputs))
+
+    def work(i):
+        try:
+            ctx = z.Context(0)
+            pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=1), ctx)
+            barrier.wait()
+            for _ in range(6):  # several rounds so the threads really overlap
+                root, data = pcs.commit([inputs[i]])
+                opened, path = pcs.mmcs.open_batch(5, data)
+                results[i] = (np.array(root), data.mats[0].to_host(), opened[0])
+                data.free()
+            ctx.close()
+        except Exception as e:  # surfaced in the main thread
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(inputs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for i, (lde, root) in enumerate(expect):
+        got_root, got_lde, got_row = results[i]
+        assert np.array_equal(got_root, root), i
+        assert np.array_equal(got_lde, lde), i
+        assert np.array_equal(got_row, lde[5]), i

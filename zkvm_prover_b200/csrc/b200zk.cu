@@ -200,11 +200,10 @@ int make_natural_map(b200zk_ctx* ctx, const uint32_t* base, uint32_t width, uint
 }
 
 bool tma_enabled() {
-    static int v = -1;
-    if (v < 0) {
+    static const int v = [] {
         const char* e = getenv("B200ZK_NTT_TMA");  // experiment knob: 0 forces the plain pass kernel
-        v = e ? atoi(e) : 1;
-    }
+        return e ? atoi(e) : 1;
+    }();
     return v != 0;
 }
 
@@ -274,9 +273,8 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             TRY(make_pass_map(ctx, p.in, width, p.in_pitch, n, s0, K, tl, &in_map));
             if (p.out_natural) TRY(make_natural_map(ctx, p.out, width, p.out_pitch, n, K, tl, &out_map));
             else TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
+            // (dynamic shared memory limits are raised once per device in configure_kernels)
             const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (2 * std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
-            CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-            CU(cudaFuncSetAttribute(ntt::pass_kernel_tma, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)NTT_TMA_CTAS * ctx->num_sms);
             ntt::pass_kernel_tma<<<grid, ntt::TMA_THREADS, tsm, ctx->stream>>>(in_map, out_map, p, (uint32_t)tiles);
             LAUNCHED();
@@ -287,12 +285,8 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         const uint64_t blocks = ((1ull << n) >> K) * col_tiles;
         if (blocks > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
         if (vec == 4) {
-            CU(cudaFuncSetAttribute(ntt::pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaFuncSetAttribute(ntt::pass_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             ntt::pass_kernel<4><<<(uint32_t)blocks, ntt::THREADS, smem, ctx->stream>>>(p);
         } else {
-            CU(cudaFuncSetAttribute(ntt::pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaFuncSetAttribute(ntt::pass_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
             ntt::pass_kernel<1><<<(uint32_t)blocks, ntt::THREADS, smem, ctx->stream>>>(p);
         }
         LAUNCHED();
@@ -342,6 +336,18 @@ extern "C" {
 
 const char* b200zk_version(void) { return "b200zk 0.1 (sm_100a)"; }
 
+// Function attributes are per device, not per ctx: they are set to the device maximum, so concurrent contexts (one per
+// host thread) can only ever write the same value and no launch depends on a value another thread may be changing.
+static int configure_kernels(int max_smem_optin) {
+    const void* big[] = {(const void*)ntt::pass_kernel_tma, (const void*)ntt::pass_kernel<4>, (const void*)ntt::pass_kernel<1>,
+                         (const void*)op::dot_ext_powers_kernel<4>, (const void*)op::dot_ext_powers_kernel<1>};
+    for (const void* f : big)
+        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return B200ZK_ERR_CUDA;
+    for (int i = 0; i < 3; i++)
+        if (cudaFuncSetAttribute(big[i], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) return B200ZK_ERR_CUDA;
+    return B200ZK_OK;
+}
+
 int b200zk_ctx_create(int device, b200zk_ctx** out) {
     if (!out) return B200ZK_ERR_ARG;
     *out = nullptr;
@@ -360,6 +366,12 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
     }
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (configure_kernels(ctx->max_smem_optin) != B200ZK_OK) {
+        cudaGetLastError();
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return B200ZK_ERR_CUDA;
+    }
     if (const char* e = getenv("B200ZK_L2_FETCH")) {  // experiment knob: L2 fetch granularity hint (32/64/128)
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
         cudaGetLastError();
@@ -1369,10 +1381,7 @@ int b200zk_mat_dot_ext_powers(b200zk_ctx* ctx, const b200zk_mat* m, const uint32
     const bool vec4 = m->width % 4 == 0 && ((uintptr_t)m->d % 16) == 0;
     const size_t smem = (size_t)((m->width + 3) / 4 * 4) * 16;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((m->rows + 8 * op::DEP_ROWS - 1) / (8 * op::DEP_ROWS), (uint64_t)ctx->num_sms * 8);
-    if (smem > 48 * 1024) {
-        CU(cudaFuncSetAttribute(op::dot_ext_powers_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(op::dot_ext_powers_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, B200ZK_ERR_SHAPE, "matrix too wide for dot_ext_powers");
     if (vec4) op::dot_ext_powers_kernel<4><<<grid, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
     else op::dot_ext_powers_kernel<1><<<grid, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
     LAUNCHED();
