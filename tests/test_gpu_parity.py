@@ -526,6 +526,58 @@ def test_max_baseline_rows_lde_commit_properties(z, ctx):
     ctx.trim()
 
 
+def test_mixed_heights_full_size_commit_and_64_openings(z, ctx):
+    """k = 3 mixed heights {2^24 x 128, 2^23 x 64, 2^20 x 40} (the inject path at BASELINE scale).
+    64 random open_batch paths are checked by the oracle's verifier and by the device verifier; the two lower layers
+    where matrices are injected are recomputed by the oracle from downloaded digests for a window of nodes."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 40 * (1 << 30):
+        pytest.skip("needs ~40 GB of free device memory")
+    shapes = [(1 << 24, 128), (1 << 23, 64), (1 << 20, 40)]
+    mats = [ctx.alloc(h, w).fill(0xC0DE + i) for i, (h, w) in enumerate(shapes)]
+    mmcs = z.MerkleTreeMmcs(ctx)
+    root, pd = mmcs.commit(mats)
+    rng = np.random.default_rng(64)
+    idxs = [0, (1 << 24) - 1] + [int(i) for i in rng.integers(0, 1 << 24, 62)]
+    heights = [h for h, _ in shapes]
+    dims = [(w, h) for h, w in shapes]
+    for idx, (rows, path) in zip(idxs, mmcs.open_batch_many(idxs, pd)):
+        assert path.shape == (24, 8)
+        for (h, w), r, m in zip(shapes, rows, mats):
+            assert np.array_equal(r, m.rows_to_host(idx >> (24 - h.bit_length() + 1), 1)[0])
+        assert O.merkle_verify(rows, heights, path, idx, root), idx
+        mmcs.verify_batch(root, dims, idx, rows, path)
+    # inject level of the 2^23 matrix: layer1[j] = compress(compress(layer0[2j], layer0[2j+1]), hash(row j of the 2^23 x 64 matrix))
+    j0 = 5_000_000
+    l0 = pd.layer(0)[2 * j0:2 * j0 + 16]
+    l1 = pd.layer(1)[j0:j0 + 8]
+    node = O.compress_pairs(l0.reshape(8, 16))
+    inj = O.hash_rows(mats[1].rows_to_host(j0, 8))
+    assert np.array_equal(O.compress_pairs(np.concatenate([node, inj], axis=1)), l1)
+    pd.free()
+    for m in mats:
+        m.free()
+    ctx.trim()
+
+
+def test_fri_commit_phase_baseline_size(z, ctx):
+    """2^25 EF4 elements folded down to blowup * final_poly_len = 2: every round's root, every
+    beta and the final folded vector equal the oracle's."""
+    ln = 25
+    vec = O.fill((1 << ln) * 4, 0xF81).reshape(-1, 4)
+    seed = rnd(8, 402)
+    c, o = z.DuplexChallenger(ctx), O.Challenger()
+    c.observe(seed)
+    o.observe(seed)
+    res = z.commit_phase(z.FriConfig(log_blowup=1, log_final_poly_len=0), [vec], c, ctx)
+    oroots, obetas, ofin = O.fri_commit_phase(vec, 1, 0, challenger=o)
+    assert len(oroots) == 24
+    assert np.array_equal(res.commits, oroots) and np.array_equal(res.betas, obetas) and np.array_equal(res.final_poly, ofin)
+    for t in res.data:
+        t.free()
+    ctx.trim()
+
+
 # ------------------------------------------------------------------------------------------ re-entrancy
 def test_concurrent_contexts_from_host_threads(z):
     """the Plonky3 objects are Clone + Sync and are called from rayon worker threads, so the
