@@ -1,5 +1,5 @@
 // Poseidon2 pipe-assignment tuning harness: times one-permutation-per-thread throughput for the knob settings
-// given with -D (P2_RC_FMA, P2_MDS_MODE, P2_INT_MODE) and checks the result against the plain formulation.
+// given with -D (P2_RC_FMA, P2_MDS_FMA_MASK, P2_INT_MODE) and checks the result against the plain formulation.
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../zkvm_prover_b200/csrc/poseidon2.cuh"
@@ -27,6 +27,6 @@ int main() {
     k<<<(n + 255) / 256, 256>>>(a, n, reps, 0); cudaDeviceSynchronize();
     cudaEventRecord(e0); k<<<(n + 255) / 256, 256>>>(a, n, reps, 0); cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    printf("RC_FMA=%d MDS_MODE=%d INT_MODE=%d  match_plain=%d  %.3f ms  %.3f Gperm/s\n", P2_RC_FMA, P2_MDS_MODE, P2_INT_MODE, ok, ms, n * reps / (ms * 1e-3) / 1e9);
+    printf("RC_FMA=%d MDS_MODE=%d INT_MODE=%d  match_plain=%d  %.3f ms  %.3f Gperm/s\n", P2_RC_FMA, P2_MDS_FMA_MASK, P2_INT_MODE, ok, ms, n * reps / (ms * 1e-3) / 1e9);
     return !ok;
 }

@@ -752,7 +752,8 @@ int b200zk_hash_rows_dev(b200zk_ctx* ctx, const b200zk_mat* m, uint32_t* d_diges
     b200zk_mat* one[1] = {const_cast<b200zk_mat*>(m)};
     uint32_t idx0 = 0;
     TRY(make_group(ctx, one, &idx0, 1, &g));
-    mk::leaf_hash_kernel<<<(uint32_t)((m->rows + 255) / 256), 256, 0, ctx->stream>>>(g, m->rows, d_digests);
+    if (g.fast8) mk::leaf_hash_fast_kernel<<<(uint32_t)((m->rows + 255) / 256), 256, 0, ctx->stream>>>(g, m->rows, d_digests);
+    else mk::leaf_hash_kernel<<<(uint32_t)((m->rows + 255) / 256), 256, 0, ctx->stream>>>(g, m->rows, d_digests);
     LAUNCHED();
     return B200ZK_OK;
 }
@@ -865,7 +866,8 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
         if (rc == B200ZK_OK && leaf_fn) {
             rc = leaf_fn(ctx, leaf_user, t->d_digests);  // the caller produces layer 0 itself (strip pipeline)
         } else if (rc == B200ZK_OK) {
-            mk::leaf_hash_kernel<<<(uint32_t)((t->max_h + 255) / 256), 256, 0, ctx->stream>>>(g, t->max_h, t->d_digests);
+            if (g.fast8) mk::leaf_hash_fast_kernel<<<(uint32_t)((t->max_h + 255) / 256), 256, 0, ctx->stream>>>(g, t->max_h, t->d_digests);
+            else mk::leaf_hash_kernel<<<(uint32_t)((t->max_h + 255) / 256), 256, 0, ctx->stream>>>(g, t->max_h, t->d_digests);
             ctx->launches++;
             if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "leaf_hash launch failed");
         }

@@ -71,15 +71,26 @@ BB_HD uint32_t sbox7(int32_t x) {
 #ifndef P2_RC_FMA
 #define P2_RC_FMA 0      // round-constant additions on the FMA pipe (1) or ALU pipe (0)
 #endif
-#ifndef P2_MDS_MODE
-#define P2_MDS_MODE 3    // how many of the linear-layer additions are steered to the FMA pipe (0 none .. 3)
+#ifndef P2_MDS_FMA_MASK
+// external linear layer: which groups of additions are steered to the FMA pipe.  bit 0: t01, t23; bit 1: the doublings;
+// bit 2: the 16 final `+ column sum`; bit 3: t0123; bit 4: t01123, t01233; bit 5: column sums; bits 6, 7: the M4 outputs
+#define P2_MDS_FMA_MASK 0x0F
+#endif
+#ifndef P2_INT_SUM_FMA
+#define P2_INT_SUM_FMA 3  // internal layer, ALU formulation: additions of the 16-lane sum steered to the FMA pipe (0 none, 1 first level, 2 +second/third, 3 all)
+#endif
+#ifndef P2_INT_LIN_FMA
+#define P2_INT_LIN_FMA 1  // internal layer: doublings (1) and the 3x additions (2) of the small diagonal multiples on the FMA pipe
+#endif
+#ifndef P2_INT_OUT_FMA
+#define P2_INT_OUT_FMA 0  // internal layer: how many of the plain `sum + x` output additions go to the FMA pipe
 #endif
 #ifndef P2_INT_MODE
 #define P2_INT_MODE 1    // internal layer: 0 = 64-bit IMAD.WIDE formulation, 1 = ALU formulation (doublings / 32-bit shifts)
 #endif
 
 BB_HD uint32_t add_f(uint32_t a, uint32_t b) { uint32_t s = bb::fadd(a, b); return bb::umin32(s, s - bb::P); }
-#define P2_ADD_LVL(lvl, a, b) ((P2_MDS_MODE >= (lvl)) ? add_f((a), (b)) : bb::add((a), (b)))
+#define P2_ADD_LVL(lvl, a, b) (((P2_MDS_FMA_MASK >> ((lvl) - 1)) & 1) ? add_f((a), (b)) : bb::add((a), (b)))
 
 // circ(2*M4, M4, M4, M4) with M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]] (p3-poseidon2 mds_light_permutation);
 // the 4x4 block uses the 11-addition schedule (t01, t23, t0123, t01123, t01233, two doublings, four sums).
@@ -89,18 +100,18 @@ BB_HD void mds_light(uint32_t (&s)[16]) {
         uint32_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
         uint32_t t01 = P2_ADD_LVL(1, x0, x1);
         uint32_t t23 = P2_ADD_LVL(1, x2, x3);
-        uint32_t t0123 = bb::add(t01, t23);
-        uint32_t t01123 = bb::add(t0123, x1);
-        uint32_t t01233 = bb::add(t0123, x3);
+        uint32_t t0123 = P2_ADD_LVL(4, t01, t23);
+        uint32_t t01123 = P2_ADD_LVL(5, t0123, x1);
+        uint32_t t01233 = P2_ADD_LVL(5, t0123, x3);
         uint32_t d0 = P2_ADD_LVL(2, x0, x0), d2 = P2_ADD_LVL(2, x2, x2);
-        s[c + 3] = bb::add(t01233, d0);           // 3x0 + x1 + x2 + 2x3
-        s[c + 1] = bb::add(t01123, d2);           // x0 + 2x1 + 3x2 + x3
-        s[c] = bb::add(t01123, t01);              // 2x0 + 3x1 + x2 + x3
-        s[c + 2] = bb::add(t01233, t23);          // x0 + x1 + 2x2 + 3x3
+        s[c + 3] = P2_ADD_LVL(7, t01233, d0);     // 3x0 + x1 + x2 + 2x3
+        s[c + 1] = P2_ADD_LVL(7, t01123, d2);     // x0 + 2x1 + 3x2 + x3
+        s[c] = P2_ADD_LVL(8, t01123, t01);        // 2x0 + 3x1 + x2 + x3
+        s[c + 2] = P2_ADD_LVL(8, t01233, t23);    // x0 + x1 + 2x2 + 3x3
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        uint32_t t = bb::add(bb::add(s[k], s[4 + k]), bb::add(s[8 + k], s[12 + k]));
+        uint32_t t = P2_ADD_LVL(6, P2_ADD_LVL(6, s[k], s[4 + k]), P2_ADD_LVL(6, s[8 + k], s[12 + k]));
 #pragma unroll
         for (int j = 0; j < 16; j += 4) s[j + k] = P2_ADD_LVL(3, s[j + k], t);
     }
@@ -146,8 +157,8 @@ BB_HD uint32_t sum16(const uint32_t (&s)[16]) {
 template <int C>
 BB_HD uint32_t lin_small(uint32_t sum, uint32_t x) {
     constexpr int A = C < 0 ? -C : C;
-    uint32_t d = bb::dbl(x);
-    uint32_t m = A == 2 ? d : (A == 3 ? bb::add(d, x) : bb::dbl(d));
+    uint32_t d = P2_INT_LIN_FMA >= 1 ? add_f(x, x) : bb::dbl(x);
+    uint32_t m = A == 2 ? d : (A == 3 ? (P2_INT_LIN_FMA >= 2 ? add_f(d, x) : bb::add(d, x)) : (P2_INT_LIN_FMA >= 1 ? add_f(d, d) : bb::dbl(d)));
     return C < 0 ? bb::sub(sum, m) : bb::add(sum, m);
 }
 template <int K>
@@ -156,29 +167,31 @@ BB_HD uint32_t div2(uint32_t x) {
     uint32_t m = (0u - x) & MASK;
     return ((x + MASK) >> K) + m * (15u << (27 - K));
 }
+#define P2_SUM_ADD(lvl, a, b) ((P2_INT_SUM_FMA >= (lvl)) ? add_f((a), (b)) : bb::add((a), (b)))
 BB_HD uint32_t sum16(const uint32_t (&s)[16]) {
-    uint32_t a0 = bb::add(s[0], s[1]), a1 = bb::add(s[2], s[3]), a2 = bb::add(s[4], s[5]), a3 = bb::add(s[6], s[7]);
-    uint32_t a4 = bb::add(s[8], s[9]), a5 = bb::add(s[10], s[11]), a6 = bb::add(s[12], s[13]), a7 = bb::add(s[14], s[15]);
-    return bb::add(bb::add(bb::add(a0, a1), bb::add(a2, a3)), bb::add(bb::add(a4, a5), bb::add(a6, a7)));
+    uint32_t a0 = P2_SUM_ADD(1, s[0], s[1]), a1 = P2_SUM_ADD(1, s[2], s[3]), a2 = P2_SUM_ADD(1, s[4], s[5]), a3 = P2_SUM_ADD(1, s[6], s[7]);
+    uint32_t a4 = P2_SUM_ADD(1, s[8], s[9]), a5 = P2_SUM_ADD(1, s[10], s[11]), a6 = P2_SUM_ADD(1, s[12], s[13]), a7 = P2_SUM_ADD(1, s[14], s[15]);
+    return P2_SUM_ADD(3, P2_SUM_ADD(2, P2_SUM_ADD(2, a0, a1), P2_SUM_ADD(2, a2, a3)), P2_SUM_ADD(2, P2_SUM_ADD(2, a4, a5), P2_SUM_ADD(2, a6, a7)));
 }
 #endif
 
+#define P2_OUT_ADD(lvl, a, b) ((P2_INT_OUT_FMA >= (lvl)) ? add_f((a), (b)) : bb::add((a), (b)))
 BB_HD void internal_round(uint32_t (&s)[16], int32_t rc) {
     s[0] = sbox7((int32_t)(P2_RC_FMA ? bb::fadd(s[0], (uint32_t)rc) : bb::aadd(s[0], (uint32_t)rc)));
     const uint32_t sum = sum16(s);
     s[0] = lin_small<-2>(sum, s[0]);
-    s[1] = bb::add(sum, s[1]);
+    s[1] = P2_OUT_ADD(1, sum, s[1]);
     s[2] = lin_small<2>(sum, s[2]);
-    s[3] = bb::add(sum, div2<1>(s[3]));
+    s[3] = P2_OUT_ADD(2, sum, div2<1>(s[3]));
     s[4] = lin_small<3>(sum, s[4]);
     s[5] = lin_small<4>(sum, s[5]);
     s[6] = bb::sub(sum, div2<1>(s[6]));
     s[7] = lin_small<-3>(sum, s[7]);
     s[8] = lin_small<-4>(sum, s[8]);
-    s[9] = bb::add(sum, div2<8>(s[9]));
-    s[10] = bb::add(sum, div2<2>(s[10]));
-    s[11] = bb::add(sum, div2<3>(s[11]));
-    s[12] = bb::add(sum, div2<27>(s[12]));
+    s[9] = P2_OUT_ADD(3, sum, div2<8>(s[9]));
+    s[10] = P2_OUT_ADD(4, sum, div2<2>(s[10]));
+    s[11] = P2_OUT_ADD(5, sum, div2<3>(s[11]));
+    s[12] = P2_OUT_ADD(6, sum, div2<27>(s[12]));
     s[13] = bb::sub(sum, div2<8>(s[13]));
     s[14] = bb::sub(sum, div2<4>(s[14]));
     s[15] = bb::sub(sum, div2<27>(s[15]));
