@@ -269,7 +269,7 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"kernel": "mk::leaf_hash_kernel (Poseidon2 sponge over the LDE rows)", "bound": "hbm", "achieved": round(leaf_bytes / (leaf_ms * 1e-3) / 1e9, 2),
+    roofline = {"kernel": "mk::leaf_hash_fast_kernel (Poseidon2 sponge over the LDE rows)", "bound": "hbm", "achieved": round(leaf_bytes / (leaf_ms * 1e-3) / 1e9, 2),
                 "peak": peak, "unit": "GB/s", "frac": round(leaf_bytes / (leaf_ms * 1e-3) / 1e9 / peak, 4), "traffic": traffic, "algorithmic_bytes": leaf_bytes, "peak_source": peak_src,
                 "ms": round(leaf_ms, 3), "share_of_step": round(leaf_ms / ms, 3), "gperm_per_s": round(perms / (leaf_ms * 1e-3) / 1e9, 3),
                 "note": "bound by the integer pipes, not HBM: 564 Montgomery products x 10 FMA-pipe clocks per permutation (32 B absorbed) put the floor at ~6.6 Gperm/s; DESIGN.md section 4",

@@ -58,6 +58,6 @@ lh = summary.get(f"leaf_hash_{R}")
 if lh:
     def num(s): return float(s.split()[0].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[s.split()[1]]
     t = num(lh[0]["dram__bytes_read.sum"]) + num(lh[0]["dram__bytes_write.sum"])
-    json.dump({"kernel": "mk::leaf_hash_kernel", "round": R, "dram_bytes_per_launch": t, "source": f"profiles/ncu_summary_{R}.json"},
+    json.dump({"kernel": "mk::leaf_hash_fast_kernel", "round": R, "dram_bytes_per_launch": t, "source": f"profiles/ncu_summary_{R}.json"},
               open(os.path.join(PR, "roofline_traffic.json"), "w"))
     print("leaf hash DRAM traffic per launch:", t / 1e9, "GB")
