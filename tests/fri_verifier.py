@@ -16,13 +16,15 @@ def verify_pcs_open(roots, dims, points, opened, proof, ch, log_blowup, log_fina
     """roots[r]: commitment (monty); dims[r]: list of (width, lde_height); points[r][i]: list of EF4 (monty);
     opened[r][i][k]: (width, 4) monty; ch: pyref DuplexChallenger in the state the prover's challenger had before open."""
     alpha = ch.sample_ext()
-    assert alpha == canon(proof["alpha"]), "alpha diverged"
+    if "alpha" in proof:  # prover-side debugging aids; a proof decoded from the wire format carries neither
+        assert alpha == canon(proof["alpha"]), "alpha diverged"
     commits = [canon(c) for c in proof["commit_phase_commits"]]
     betas = []
     for c in commits:
         ch.observe_slice(c)
         betas.append(ch.sample_ext())
-    assert betas == [canon(b) for b in proof["betas"]]
+    if "betas" in proof:
+        assert betas == [canon(b) for b in proof["betas"]]
     final_poly = [canon(c) for c in proof["final_poly"]]
     for c in final_poly:
         ch.observe_slice(c)
@@ -30,8 +32,10 @@ def verify_pcs_open(roots, dims, points, opened, proof, ch, log_blowup, log_fina
     log_max = proof["log_max_height"]
     n_rounds = len(commits)
     assert n_rounds == log_max - log_blowup - log_final_poly_len
-    for q, index in enumerate(proof["query_indices"]):
-        assert index == ch.sample_bits(log_max), "query index diverged"
+    for q in range(len(proof["input_openings"][0])):
+        index = ch.sample_bits(log_max)
+        if "query_indices" in proof:
+            assert index == proof["query_indices"][q], "query index diverged"
         ro, num_reduced = {}, {}
         for r, root in enumerate(roots):
             vals, path = proof["input_openings"][r][q]
@@ -58,8 +62,13 @@ def verify_pcs_open(roots, dims, points, opened, proof, ch, log_blowup, log_fina
             lfh = log_max - i - 1
             idx_i = index >> i
             pair, path = proof["commit_phase_openings"][i][q]
-            evals = [canon(pair[0]), canon(pair[1])]
-            assert evals[idx_i & 1] == folded, f"query {q}: folded value does not match the committed layer {i}"
+            if proof.get("sibling_only"):  # p3-fri's CommitPhaseProofStep: only the sibling travels, the Merkle check binds the folded value
+                evals = [None, None]
+                evals[idx_i & 1] = folded
+                evals[1 - (idx_i & 1)] = canon(pair)
+            else:
+                evals = [canon(pair[0]), canon(pair[1])]
+                assert evals[idx_i & 1] == folded, f"query {q}: folded value does not match the committed layer {i}"
             assert R.verify_batch([evals[0] + evals[1]], [1 << lfh], [canon(p) for p in path], idx_i >> 1, commits[i]), "commit-phase opening rejected"
             x = pow(R.two_adic_generator(lfh + 1), R.bitrev(idx_i >> 1, lfh), P)
             e0, e1 = evals

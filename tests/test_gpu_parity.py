@@ -431,6 +431,21 @@ def test_pcs_open_end_to_end_accepted_by_independent_verifier(z, ctx, lf):
                 assert np.array_equal(opened[r][i][k], O.interpolate_coset_bitrev(lde[:n], z.GENERATOR_MONTY, pt))
     dims = [[(w, n << lb) for (n, w) in rs] for rs in shapes]
     assert V.verify_pcs_open([root for root, _ in commits], dims, points, opened, proof, pc, lb, lf, pow_bits)
+    # the same proof through the reference's wire format (p3-fri FriProof, bincode v1): encode, decode, verify again
+    from zkvm_prover_b200 import proof as W
+    blob = W.FriProof.from_pcs_open(proof).encode()
+    dec = W.FriProof.decode(blob)
+    assert dec.encode() == blob and dec.pow_witness == proof["pow_witness"] and len(dec.query_proofs) == nq
+    wire = {"commit_phase_commits": dec.commit_phase_commits, "final_poly": dec.final_poly, "pow_witness": dec.pow_witness,
+            "log_max_height": proof["log_max_height"], "sibling_only": True,
+            "input_openings": [[(qp.input_proof[r].opened_values, qp.input_proof[r].opening_proof) for qp in dec.query_proofs] for r in range(len(commits))],
+            "commit_phase_openings": [[(qp.commit_phase_openings[i].sibling_value, qp.commit_phase_openings[i].opening_proof) for qp in dec.query_proofs]
+                                      for i in range(len(dec.commit_phase_commits))]}
+    pcw = R.DuplexChallenger()
+    for root, _ in commits:
+        pcw.observe_slice(O.from_monty(root).tolist())
+    pcw.sample_ext()
+    assert V.verify_pcs_open([root for root, _ in commits], dims, points, opened, wire, pcw, lb, lf, pow_bits)
     # a corrupted opened value must be rejected
     bad = [[[y.copy() for y in m] for m in rr] for rr in opened]
     bad[0][0][0][0, 0] ^= 1

@@ -1,0 +1,118 @@
+"""Wire-format parity: the legacy bincode `VmInternalStarkProof` encoding of the reference
+(/root/reference/crates/types/src/proof.rs:70-74).  CPU-only; no oracle arithmetic is involved."""
+import base64
+import glob
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from zkvm_prover_b200 import proof as W
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "proof_codec.json")))
+REF = "/root/reference/crates/verifier/testdata/proofs"
+P = 0x78000001
+
+
+def _rnd(rng, *shape):
+    return rng.integers(0, P, shape, dtype=np.uint64).astype(np.uint32)
+
+
+def _random_proof(rng, n_air=3, n_q=2, rounds=3, logup=True):
+    def adj(w):
+        return W.AdjacentOpenedValues(_rnd(rng, w, 4), _rnd(rng, w, 4))
+
+    def batch(widths, depth):
+        return W.BatchOpening([_rnd(rng, w) for w in widths], _rnd(rng, depth, 8))
+
+    queries = [W.QueryProof([batch([5, 1, 9], 7), batch([12], 4)],
+                            [W.CommitPhaseProofStep(_rnd(rng, 4), _rnd(rng, rounds - i, 8)) for i in range(rounds)]) for _ in range(n_q)]
+    fri = W.FriProof(_rnd(rng, rounds, 8), queries, _rnd(rng, 2, 4), int(rng.integers(0, P)))
+    opened = W.OpenedValues([adj(2)], [[adj(3), adj(0)], [adj(7)]], [[adj(4)] * n_air], [[_rnd(rng, 4, 4), _rnd(rng, 4, 4)], [_rnd(rng, 4, 4)]])
+    per_air = [W.AirProofData(i, 1 << (i + 2), [_rnd(rng, i, 4)], _rnd(rng, 2 * i)) for i in range(n_air)]
+    return W.Proof(_rnd(rng, 2, 8), _rnd(rng, 1, 8), _rnd(rng, 8), fri, opened, per_air, 1234567 if logup else None)
+
+
+def _eq(a, b):
+    if isinstance(a, np.ndarray):
+        return isinstance(b, np.ndarray) and a.shape == b.shape and np.array_equal(a, b)
+    if isinstance(a, list):
+        return isinstance(b, list) and len(a) == len(b) and all(_eq(x, y) for x, y in zip(a, b))
+    if hasattr(a, "__dataclass_fields__"):
+        return type(a) is type(b) and all(_eq(getattr(a, k), getattr(b, k)) for k in a.__dataclass_fields__)
+    return a == b
+
+
+@pytest.mark.parametrize("logup", [True, False])
+def test_synthetic_round_trip(logup):
+    rng = np.random.default_rng(5)
+    v = W.VmInternalStarkProof([_random_proof(rng, logup=logup), _random_proof(rng, n_air=1, n_q=1, rounds=1, logup=logup)], _rnd(rng, 32))
+    blob, pv = v.encode_proofs(), v.encode_public_values()
+    back = W.VmInternalStarkProof.decode(blob, pv)
+    assert _eq(back, v)
+    assert back.encode_proofs() == blob and back.encode_public_values() == pv
+    assert _eq(W.VmInternalStarkProof.from_json_fields(v.to_json_fields()), v)
+    # layout spot checks (bincode v1): Vec length as u64, digests without a length prefix, Option tag last
+    assert blob[:8] == (2).to_bytes(8, "little") and blob[8:16] == (2).to_bytes(8, "little")
+    assert np.array_equal(np.frombuffer(blob[16:48], "<u4"), v.proofs[0].main_trace_commits[0])
+    assert blob[-5 if logup else -1] == (1 if logup else 0)
+    fb = v.proofs[0].fri.encode()
+    assert _eq(W.FriProof.decode(fb), v.proofs[0].fri)
+
+
+def test_malformed_input_is_rejected():
+    rng = np.random.default_rng(6)
+    blob = W.VmInternalStarkProof([_random_proof(rng)]).encode_proofs()
+    with pytest.raises(ValueError):
+        W.VmInternalStarkProof.decode(blob[:-3])                       # truncated
+    with pytest.raises(ValueError):
+        W.VmInternalStarkProof.decode(blob + b"\0")                     # trailing bytes
+    with pytest.raises(ValueError):
+        W.VmInternalStarkProof.decode((1 << 60).to_bytes(8, "little"))  # absurd length must not allocate
+    bad = bytearray(blob)
+    bad[-5] = 7                                                         # Option tag
+    with pytest.raises(ValueError):
+        W.VmInternalStarkProof.decode(bytes(bad))
+    with pytest.raises(ValueError):
+        W.CommitPhaseProofStep(np.zeros(3, np.uint32), np.zeros((0, 8), np.uint32)).write(W._Writer())  # an EF4 has four coefficients
+
+
+def test_golden_summary_is_consistent():
+    fx = GOLD["fixtures"]
+    assert {"chunk-proof-phase2.json", "chunk-proof-phase1.json", "chunk-proof-feynman.json"} <= set(fx)
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chunk_proof_phase2_kats.json")))
+    g = fx["chunk-proof-phase2.json"]
+    assert g["file_sha256"] == kats["sha256"] and g["degrees"] == kats["degrees"]   # the same file the Merkle/FRI/LDE KATs were mined from
+    assert g["n_airs"] == 17 and g["n_proofs"] == 1 and g["n_public_values"] == 32
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference fixtures are only mounted in the build container")
+def test_reference_fixtures_reencode_byte_identically():
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(REF, "*-proof-*.json"))):
+        name = os.path.basename(path)
+        if name not in GOLD["fixtures"]:
+            continue
+        g = GOLD["fixtures"][name]
+        pr = json.load(open(path))["proof"]
+        blob, pv = base64.b64decode(pr["proofs"]), base64.b64decode(pr["public_values"])
+        assert hashlib.sha256(blob).hexdigest() == g["proofs_sha256"]
+        v = W.VmInternalStarkProof.decode(blob, pv)
+        assert v.encode_proofs() == blob and v.encode_public_values() == pv
+        assert v.to_json_fields() == {"proofs": pr["proofs"], "public_values": pr["public_values"]}
+        p = v.proofs[0]
+        assert [a.degree for a in p.per_air] == g["degrees"] and len(p.fri.query_proofs) == g["n_queries"]
+        assert p.fri.pow_witness == g["pow_witness"] and p.quotient_commit.tolist() == g["quotient_commit"]
+        # structure implied by the FRI parameters: round r opens a tree of height log_max - 1 - r
+        log_max = max(g["degrees"]).bit_length() - 1 + 2
+        for qp in p.fri.query_proofs:
+            assert [len(s.opening_proof) for s in qp.commit_phase_openings] == [log_max - 1 - r for r in range(g["fri_rounds"])]
+        if name == "chunk-proof-phase2.json":  # the opening the Merkle KAT B-3 was mined from (tests/golden/chunk_proof_phase2_kats.json)
+            kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chunk_proof_phase2_kats.json")))
+            b = p.fri.query_proofs[0].input_proof[2]
+            assert b.opened_values[0].tolist() == kats["b3_single_matrix"]["row"] and b.opening_proof.tolist() == kats["b3_single_matrix"]["path"]
+            assert p.main_trace_commits[0].tolist() == kats["b3_single_matrix"]["root"]
+        seen += 1
+    assert seen == len(GOLD["fixtures"])

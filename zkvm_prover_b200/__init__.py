@@ -21,3 +21,5 @@ from .symmetric import Poseidon2BabyBear16, PaddingFreeSponge, TruncatedPermutat
 from .mmcs import MerkleTreeMmcs, ExtensionMmcs, ProverData  # noqa: F401
 from .challenger import DuplexChallenger  # noqa: F401
 from .fri import FriConfig, TwoAdicFriPcs, commit_phase, fold_matrix  # noqa: F401
+from . import field, proof  # noqa: F401
+from .proof import FriProof, VmInternalStarkProof  # noqa: F401

@@ -274,7 +274,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             if (p.out_natural) TRY(make_natural_map(ctx, p.out, width, p.out_pitch, n, K, tl, &out_map));
             else TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
             // (dynamic shared memory limits are raised once per device in configure_kernels)
-            const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (2 * std::max<uint64_t>(R / 2, 1) + 2 * R) * 4;
+            const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (2 * std::max<uint64_t>(R / 2, 1) + 4 * R) * 4;
             const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)NTT_TMA_CTAS * ctx->num_sms);
             ntt::pass_kernel_tma<<<grid, ntt::TMA_THREADS, tsm, ctx->stream>>>(in_map, out_map, p, (uint32_t)tiles);
             LAUNCHED();

@@ -70,6 +70,16 @@ __device__ __forceinline__ uint32_t pow2level(const uint32_t* lo, const uint32_t
     return bb::mul(l, __ldg(hi + (e >> LO_BITS)));  // hi[] may carry a scale factor, so always multiply
 }
 
+// Shoup product with a precomputed pair (w, w' = floor(w 2^32 / p)), w a PLAIN integer < p: d*w mod p for any 32-bit d, so
+// Montgomery-form data stays in Montgomery form.  IMAD.HI + 2 IMAD (8 FMA-pipe clocks, a Montgomery product needs 10) and
+// one ALU instruction (Montgomery: two).
+__device__ __forceinline__ uint32_t shoup_mul(uint32_t d, uint2 w) {
+    const uint32_t q = __umulhi(d, w.y);
+    return bb::red2p(d * w.x - q * bb::P);
+}
+// the pair for a factor given in Montgomery form f = w 2^32 mod p:  w 2^32 = w' p + f  =>  w' = -f p^-1 (mod 2^32)
+__device__ __forceinline__ uint2 shoup_pair(uint32_t f_monty) { return make_uint2(bb::from_monty(f_monty), (0u - f_monty) * bb::MU); }
+
 // k stages (radix 2^k) at local stage u of the 2^K-point DIF, on registers; sm = tile [2^K][TILE_COLS]
 // LAST: this round ends the tile's DIF (lowbits == 0), so the twiddle index of a butterfly depends only on q and the
 // butterflies with (q & (half-1)) == 0 multiply by w^0 = 1: they are done as plain subtractions (7 of the 12 butterflies
@@ -77,8 +87,8 @@ __device__ __forceinline__ uint32_t pow2level(const uint32_t* lo, const uint32_t
 // BREV_OUT (final round of a scatter pass, TMA kernel only): row t' is written to slot bitrev_K(t') so the tile leaves in
 // natural coefficient order; every thread has exactly one group then, and a named barrier separates loads from stores.
 template <int k, int VEC, bool LAST, int NT = THREADS, bool BREV_OUT = false>
-__device__ __forceinline__ void radix_round(uint32_t* sm, const uint2* sm_tw, int K, int lc, int u, int tid, const uint32_t* fac_pre = nullptr,
-                                            const uint32_t* fac_post = nullptr) {
+__device__ __forceinline__ void radix_round(uint32_t* sm, const uint2* sm_tw, int K, int lc, int u, int tid, const uint2* fac_pre = nullptr,
+                                            const uint2* fac_post = nullptr) {
     constexpr int LV = VEC == 4 ? 2 : 0;
     const int ll = lc - LV;                 // log2(threads per row)
     const int TILE_COLS = 1 << lc;
@@ -96,9 +106,9 @@ __device__ __forceinline__ void radix_round(uint32_t* sm, const uint2* sm_tw, in
         if (fac_pre) {
 #pragma unroll
             for (int q = 0; q < R; q++) {
-                const uint32_t f = fac_pre[base + (q << lowbits)];
+                const uint2 f = fac_pre[base + (q << lowbits)];
 #pragma unroll
-                for (int c = 0; c < VEC; c++) x[q].v[c] = bb::mul(x[q].v[c], f);
+                for (int c = 0; c < VEC; c++) x[q].v[c] = shoup_mul(x[q].v[c], f);
             }
         }
 #pragma unroll
@@ -134,9 +144,9 @@ __device__ __forceinline__ void radix_round(uint32_t* sm, const uint2* sm_tw, in
         if (fac_post) {
 #pragma unroll
             for (int q = 0; q < R; q++) {
-                const uint32_t f = fac_post[base + (q << lowbits)];
+                const uint2 f = fac_post[base + (q << lowbits)];
 #pragma unroll
-                for (int c = 0; c < VEC; c++) x[q].v[c] = bb::mul(x[q].v[c], f);
+                for (int c = 0; c < VEC; c++) x[q].v[c] = shoup_mul(x[q].v[c], f);
             }
         }
         if (BREV_OUT) {
@@ -335,7 +345,7 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
     uint64_t* done = full + TMA_STAGES;                                            // [3] consumers finished the tile
     uint32_t* bufs = reinterpret_cast<uint32_t*>(smem_raw + 128);                  // TMA_STAGES tiles, each 128-B aligned
     uint2* sm_tw = reinterpret_cast<uint2*>(bufs + TMA_STAGES * (tile_bytes / 4));  // [R/2] local roots (Shoup pairs)
-    uint32_t* sm_fac = reinterpret_cast<uint32_t*>(sm_tw + (R > 1 ? R / 2 : 1));    // [2][R] prescale / twist per row
+    uint2* sm_fac = sm_tw + (R > 1 ? R / 2 : 1);                                   // [2][R] prescale / twist per row (Shoup pairs)
     const int tid = threadIdx.x;
     const uint32_t col_tiles = (p.width + (1u << lc) - 1) >> lc;
 
@@ -407,22 +417,22 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
         const uint64_t row_base = (high << (n - s0)) + low;
         const bool need_twist = L > 0 && low != 0;
         // per-row factors for this tile (tables are L2/L1 resident); double-buffered by tile parity
-        uint32_t* fac_pre = p.pre_lo ? sm_fac : nullptr;
-        uint32_t* fac_post = need_twist ? sm_fac + R : nullptr;
+        uint2* fac_pre = p.pre_lo ? sm_fac : nullptr;
+        uint2* fac_post = need_twist ? sm_fac + R : nullptr;
         asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");  // previous tile's factors are no longer read
         for (int t = tid; t < R; t += TMA_CONSUMERS) {
-            if (fac_pre) fac_pre[t] = pow2level(p.pre_lo, p.pre_hi, row_base + ((uint64_t)t << L));
+            if (fac_pre) fac_pre[t] = shoup_pair(pow2level(p.pre_lo, p.pre_hi, row_base + ((uint64_t)t << L)));
             if (fac_post) {
                 uint64_t e = (low * (uint64_t)bb::bitrev((uint32_t)t, K)) << s0;
                 if (p.inverse) e = ((1ull << n) - e) & ((1ull << n) - 1);
-                fac_post[t] = pow2level(p.tw_lo, p.tw_hi, e);
+                fac_post[t] = shoup_pair(pow2level(p.tw_lo, p.tw_hi, e));
             }
         }
         mbar_wait(full + b, (c / TMA_STAGES) & 1);
         asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");  // factors visible to every consumer
         int u = 0;
-        const uint32_t* pre = fac_pre;
-        auto post_if_last = [&](int stages) { return (u + stages == K) ? (const uint32_t*)fac_post : (const uint32_t*)nullptr; };
+        const uint2* pre = fac_pre;
+        auto post_if_last = [&](int stages) { return (u + stages == K) ? (const uint2*)fac_post : (const uint2*)nullptr; };
         const bool brev = p.out_natural != 0;
         if (rem == 1) {
             if (K == 1 && brev) radix_round<1, 4, true, TMA_CONSUMERS, true>(sm, sm_tw, K, lc, u, tid, pre, post_if_last(1));
