@@ -541,6 +541,31 @@ def test_max_baseline_rows_lde_commit_properties(z, ctx):
     ctx.trim()
 
 
+def test_largest_baseline_config_2pow24_x512(z, ctx):
+    """BASELINE's largest shape: 2^24 x 512 trace (34 GB) -> 2^25 x 512 LDE (69 GB) + commit, resident on one GPU with no
+    scratch beyond the output.  Checks: shift-1 containment of the input and a verified opening at a
+    high index (byte offsets reach 2^36 here)."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 125 * (1 << 30):
+        pytest.skip("needs ~125 GB of free device memory")
+    n, w = 24, 512
+    m = ctx.alloc(1 << n, w).fill(512)
+    pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=1), ctx)
+    root, pd = pcs.commit([m], domain_shifts=[31])          # shift = GENERATOR / 31 = 1: the LDE contains the trace
+    lde = pd.mats[0]
+    assert (lde.rows, lde.width) == (1 << 25, w)
+    for j in (0, 7, (1 << n) - 1, 9_999_999):
+        i = int(format(j, f"0{n}b")[::-1], 2)
+        assert np.array_equal(lde.rows_to_host(j, 1), m.rows_to_host(i, 1)), j
+    idx = (1 << 25) - 3
+    rows, path = pcs.mmcs.open_batch(idx, pd)
+    assert len(path) == 25 and O.merkle_verify(rows, [1 << 25], path, idx, root)
+    pcs.mmcs.verify_batch(root, [(w, 1 << 25)], idx, rows, path)
+    pd.free()
+    m.free()
+    ctx.trim()
+
+
 def test_mixed_heights_full_size_commit_and_64_openings(z, ctx):
     """k = 3 mixed heights {2^24 x 128, 2^23 x 64, 2^20 x 40} (the inject path at BASELINE scale).
     64 random open_batch paths are checked by the oracle's verifier and by the device verifier; the two lower layers
