@@ -514,6 +514,7 @@ def test_max_baseline_rows_lde_commit_properties(z, ctx):
     rows whose bit-reversed index is even, the strip-pipelined host path agrees with the resident path on a column
     subset, and an opening at a high index verifies (device + oracle verifier)."""
     import torch
+    ctx.trim()   # give cached blocks back before measuring free memory
     if torch.cuda.mem_get_info()[0] < 60 * (1 << 30):
         pytest.skip("needs ~60 GB of free device memory")
     n, w = 24, 128
@@ -546,6 +547,7 @@ def test_largest_baseline_config_2pow24_x512(z, ctx):
     scratch beyond the output.  Checks: shift-1 containment of the input and a verified opening at a
     high index (byte offsets reach 2^36 here)."""
     import torch
+    ctx.trim()   # give cached blocks back before measuring free memory
     if torch.cuda.mem_get_info()[0] < 125 * (1 << 30):
         pytest.skip("needs ~125 GB of free device memory")
     n, w = 24, 512
@@ -571,6 +573,7 @@ def test_mixed_heights_full_size_commit_and_64_openings(z, ctx):
     64 random open_batch paths are checked by the oracle's verifier and by the device verifier; the two lower layers
     where matrices are injected are recomputed by the oracle from downloaded digests for a window of nodes."""
     import torch
+    ctx.trim()   # give cached blocks back before measuring free memory
     if torch.cuda.mem_get_info()[0] < 40 * (1 << 30):
         pytest.skip("needs ~40 GB of free device memory")
     shapes = [(1 << 24, 128), (1 << 23, 64), (1 << 20, 40)]

@@ -49,8 +49,12 @@ roots = []
 for seg in mine:
     for i, t in enumerate(traces):  # a different witness per segment
         t.fill(g["seed_base"] + 1000 * (seg + 1) + i)
+    ts = time.perf_counter()
     root, proof = prove_segment(seg, traces)
     roots.append(root)
+    if os.environ.get("SEGMENT_TIMES"):
+        ctx.sync()
+        print(f"rank {rank} segment {seg}: {1e3 * (time.perf_counter() - ts):.1f} ms", flush=True)
 ctx.sync(); torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], device="cuda")
 if world > 1:

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/b200zk.h"
@@ -43,6 +44,9 @@ struct b200zk_ctx {
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), null if unavailable
     cudaStream_t copy_stream = nullptr;  // host->device strip copies of b200zk_lde_commit_host (created on first use)
     cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    std::unordered_multimap<size_t, void*> cache;   // freed blocks by (rounded) size, see dev_alloc
+    std::unordered_map<void*, size_t> live;         // blocks handed out by dev_alloc
+    size_t cache_bytes = 0, cache_cap = 0;
 };
 struct b200zk_mat {
     uint32_t* d = nullptr;
@@ -96,22 +100,63 @@ inline int log2u(uint64_t x) {
     return l;
 }
 
+// Device memory comes from the stream-ordered pool (release threshold = never), fronted by an exact-size block cache per
+// ctx: a prover repeats the same allocation sizes segment after segment, and even a pool hit costs 2-5 ms for a GB-sized
+// block (50-70 ms when the pool has to grow; measured with the real 17-AIR segment shape), while a cache hit costs a
+// hash lookup.  Reuse is safe because every consumer of a block is ordered on ctx->stream (the copy stream of the host
+// strip pipeline synchronises with it through events before a buffer is released).  The cache holds at most half of the
+// device memory, is emptied by b200zk_ctx_trim, and is flushed automatically when the pool reports out-of-memory.
+void cache_flush(b200zk_ctx* ctx) {
+    for (auto& kv : ctx->cache) cudaFreeAsync(kv.second, ctx->stream);
+    ctx->cache.clear();
+    ctx->cache_bytes = 0;
+}
 int dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
     *out = nullptr;
     if (!bytes) bytes = 16;
-    // stream-ordered pool allocation (release threshold = never): after warm-up an allocation costs
-    // microseconds instead of the tens of milliseconds cudaMalloc/cudaFree take for GB-sized buffers
+    bytes = (bytes + 511) & ~(size_t)511;
+    auto it = ctx->cache.find(bytes);
+    if (it != ctx->cache.end()) {
+        *out = it->second;
+        ctx->cache.erase(it);
+        ctx->cache_bytes -= bytes;
+        ctx->live.emplace(*out, bytes);
+        return B200ZK_OK;
+    }
     cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+    if (e == cudaErrorMemoryAllocation && !ctx->cache.empty()) {  // give the cached blocks back and try once more
+        cudaGetLastError();
+        cache_flush(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        e = cudaMallocAsync(out, bytes, ctx->stream);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
+        *out = nullptr;
         return fail(ctx, B200ZK_ERR_OOM, "cudaMallocAsync(" + std::to_string(bytes) + "): " + cudaGetErrorString(e));
     }
+    ctx->live.emplace(*out, bytes);
     return B200ZK_OK;
 }
 void dev_free(b200zk_ctx* ctx, void* p) {
     if (!p) return;
-    if (ctx && ctx->stream) cudaFreeAsync(p, ctx->stream);
-    else cudaFree(p);
+    if (!ctx || !ctx->stream) {
+        cudaFree(p);
+        return;
+    }
+    auto it = ctx->live.find(p);
+    if (it == ctx->live.end()) {  // not from dev_alloc
+        cudaFreeAsync(p, ctx->stream);
+        return;
+    }
+    const size_t bytes = it->second;
+    ctx->live.erase(it);
+    if (ctx->cache_cap && ctx->cache_bytes + bytes <= ctx->cache_cap) {
+        ctx->cache.emplace(bytes, p);
+        ctx->cache_bytes += bytes;
+    } else {
+        cudaFreeAsync(p, ctx->stream);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- twiddles
@@ -390,6 +435,13 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
         }
         cudaGetLastError();
     }
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_cap = total_b / 2;
+        if (const char* e = getenv("B200ZK_ALLOC_CACHE"))  // experiment knob: 0 disables the block cache
+            if (atoi(e) == 0) ctx->cache_cap = 0;
+        cudaGetLastError();
+    }
     if (cudaMalloc((void**)&ctx->d_small, 65536) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -403,6 +455,7 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cache_flush(ctx);
     for (auto& dir : ctx->tw_local)
         for (auto& p : dir) cudaFree(p);
     for (auto& p : ctx->tw_lo) cudaFree(p);
@@ -428,6 +481,7 @@ int b200zk_ctx_sync(b200zk_ctx* ctx) {
 int b200zk_ctx_trim(b200zk_ctx* ctx) {
     if (!ctx) return B200ZK_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
+    cache_flush(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
@@ -932,7 +986,69 @@ int b200zk_lde_commit(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uin
     if (!k || !evals || !shifts) return fail(ctx, B200ZK_ERR_ARG, "no matrices");
     std::vector<b200zk_mat*> ldes(k, nullptr);
     int rc = B200ZK_OK;
-    for (uint32_t i = 0; i < k && rc == B200ZK_OK; i++) rc = b200zk_coset_lde_batch(ctx, evals[i], added_bits, shifts[i], 1, &ldes[i]);
+    for (uint32_t i = 0; i < k && rc == B200ZK_OK; i++) rc = check_mat(ctx, evals[i]);
+    // Real traces are many narrow matrices of a few heights (the reference fixture: 17 AIRs, widths 1..398).  The transform
+    // is column-independent, so all matrices of one (height, shift) class are extended as ONE matrix: their columns are
+    // gathered side by side into a work matrix (pitch a multiple of 4), extended with full-width tiles, and the result is
+    // scattered into each matrix's own tightly packed LDE (the Merkle leaves stay separate row-major matrices).
+    std::vector<char> done(k, 0);
+    for (uint32_t i = 0; i < k && rc == B200ZK_OK; i++) {
+        if (done[i]) continue;
+        std::vector<uint32_t> grp;
+        uint64_t wt = 0;
+        for (uint32_t j = i; j < k; j++)
+            if (!done[j] && evals[j]->rows == evals[i]->rows && shifts[j] == shifts[i]) {
+                grp.push_back(j);
+                wt += evals[j]->width;
+            }
+        const uint64_t N = evals[i]->rows;
+        const uint64_t M = N << added_bits;
+        const uint64_t wp = (wt + 3) & ~3ull;
+        static const bool group_on = [] {
+            const char* e = getenv("B200ZK_LDE_GROUP");  // experiment knob: 0 extends every matrix on its own
+            return !e || atoi(e) != 0;
+        }();
+        if (!group_on) {
+            grp.assign(1, i);
+            wt = evals[i]->width;
+        }
+        const bool grouped = group_on && (grp.size() > 1 || evals[i]->width % 4 != 0) && is_pow2(N) && N >= 2 && N * wt >= (1ull << 14) && M * wp * 4 <= (8ull << 30) &&
+                             log2u(N) + (int)added_bits <= MAX_LOG && shifts[i] != 0 && shifts[i] < bb::P;
+        if (!grouped) {  // a single aligned matrix (the benchmark shape), tiny inputs, and every error case: the plain entry point
+            rc = b200zk_coset_lde_batch(ctx, evals[i], added_bits, shifts[i], 1, &ldes[i]);
+            done[i] = 1;
+            continue;
+        }
+        CU(cudaSetDevice(ctx->device));
+        const int n = log2u(N);
+        uint32_t *pin = nullptr, *pout = nullptr;
+        rc = dev_alloc(ctx, N * wp * 4, (void**)&pin);
+        if (rc == B200ZK_OK) rc = dev_alloc(ctx, M * wp * 4, (void**)&pout);
+        if (rc == B200ZK_OK) rc = lde_tables(ctx, n, added_bits, shifts[i]);
+        uint64_t off = 0;
+        for (size_t g = 0; g < grp.size() && rc == B200ZK_OK; g++) {
+            const b200zk_mat* m = evals[grp[g]];
+            const uint32_t dw = m->width + (g + 1 == grp.size() ? (uint32_t)(wp - wt) : 0u);  // the last one also writes the zero padding
+            repitch_kernel<<<(uint32_t)((N * dw + 255) / 256), 256, 0, ctx->stream>>>(m->d, m->width, m->width, pin + off, (uint32_t)wp, dw, N);
+            ctx->launches++;
+            off += m->width;
+        }
+        if (rc == B200ZK_OK) rc = lde_core(ctx, pin, (uint32_t)wp, n, (uint32_t)wp, added_bits, pout, (uint32_t)wp);
+        off = 0;
+        for (size_t g = 0; g < grp.size() && rc == B200ZK_OK; g++) {
+            const uint32_t j = grp[g];
+            rc = b200zk_mat_alloc(ctx, M, evals[j]->width, &ldes[j]);
+            if (rc != B200ZK_OK) break;
+            const uint32_t w = evals[j]->width;
+            repitch_kernel<<<(uint32_t)((M * w + 255) / 256), 256, 0, ctx->stream>>>(pout + off, (uint32_t)wp, w, ldes[j]->d, w, w, M);
+            ctx->launches++;
+            off += w;
+        }
+        if (rc == B200ZK_OK && cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "column gather/scatter launch failed");
+        dev_free(ctx, pin);
+        dev_free(ctx, pout);
+        for (uint32_t j : grp) done[j] = 1;
+    }
     if (rc == B200ZK_OK) rc = b200zk_merkle_commit(ctx, ldes.data(), k, /*take=*/1, h_root, out);
     if (rc != B200ZK_OK)
         for (auto* m : ldes) b200zk_mat_free(ctx, m);

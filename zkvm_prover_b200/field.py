@@ -73,3 +73,41 @@ def ef_pow(a, e: int):
         b = ef_mul(b, b)
         e >>= 1
     return r
+
+
+# ---- vectorised EF4 helpers (numpy, canonical uint64 inside): the per-column glue of the open phase
+def _ef_mul_canon(a, b):
+    """a, b: (..., 4) canonical uint64 arrays -> (..., 4) canonical"""
+    p = np.uint64(P)
+    pr = [[(a[..., i] * b[..., j]) % p for j in range(4)] for i in range(4)]   # 31-bit x 31-bit fits in 64 bits
+    w = np.uint64(11)
+    c0 = (pr[0][0] + w * ((pr[1][3] + pr[2][2] + pr[3][1]) % p)) % p
+    c1 = (pr[0][1] + pr[1][0] + w * ((pr[2][3] + pr[3][2]) % p)) % p
+    c2 = (pr[0][2] + pr[1][1] + pr[2][0] + w * pr[3][3]) % p
+    c3 = (pr[0][3] + pr[1][2] + pr[2][1] + pr[3][0]) % p
+    return np.stack([c0, c1, c2, c3], axis=-1)
+
+
+def _canon_arr(a):
+    return (np.asarray(a, dtype=np.uint64) * np.uint64(_RINV)) % np.uint64(P)
+
+
+def ef_powers(a, n: int):
+    """[a^0, a^1, ..., a^(n-1)] as an (n, 4) Montgomery array (doubling: log2 n vectorised products)"""
+    base = _canon_arr(a).reshape(4)
+    pw = np.zeros((1, 4), np.uint64)
+    pw[0, 0] = 1
+    step = base.copy()                       # a^len(pw)
+    while pw.shape[0] < n:
+        pw = np.concatenate([pw, _ef_mul_canon(pw, step[None, :])], axis=0)
+        step = _ef_mul_canon(step, step)
+    return to_monty(pw[:n])
+
+
+def ef_dot(a, b):
+    """sum_i a[i] * b[i] for (n, 4) Montgomery arrays -> EF4 (Montgomery)"""
+    a, b = _canon_arr(a).reshape(-1, 4), _canon_arr(b).reshape(-1, 4)
+    if a.shape[0] == 0:
+        return np.zeros(4, np.uint32)
+    prod = _ef_mul_canon(a, b)
+    return to_monty(prod.sum(axis=0) % np.uint64(P))   # at most 2^33 terms of 31 bits would fit; widths are << that

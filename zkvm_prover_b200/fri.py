@@ -9,7 +9,7 @@ import numpy as np
 
 from .challenger import DuplexChallenger
 from .device import Context, DeviceBuffer, DeviceMatrix, default_context
-from .field import GENERATOR_MONTY, P, ef_add, ef_mul, ef_pow, ef_scale_base, monty_scalar, two_adic_generator
+from .field import GENERATOR_MONTY, P, ef_add, ef_dot, ef_mul, ef_pow, ef_powers, ef_scale_base, monty_scalar, two_adic_generator
 from .mmcs import DIGEST, MerkleTreeMmcs, ProverData
 
 
@@ -206,6 +206,8 @@ class TwoAdicFriPcs:
          -- the arithmetic of every step is."""
         alpha = challenger.sample_algebra_element()
         reduced, num_reduced, opened, keep = {}, {}, [], []
+        alpha_pows = np.zeros((0, 4), np.uint32)
+        inv_cache = {}
         for pd, points in rounds:
             per_round = []
             for lde, pts in zip(pd.mats, points):
@@ -216,18 +218,18 @@ class TwoAdicFriPcs:
                 rr = self.dot_ext_powers(lde, alpha)
                 per_mat = []
                 for zpt in pts:
-                    inv = self.inv_denominators(lh, zpt)
+                    key = (lh, np.asarray(zpt, np.uint32).tobytes())
+                    if key not in inv_cache:               # matrices of one height share 1 / (z - x) for a common point
+                        inv_cache[key] = self.inv_denominators(lh, zpt)
+                    inv = inv_cache[key]
                     ys = self.interpolate_coset(lde, zpt, inv)
-                    rys = np.zeros(4, np.uint32)
-                    apw = np.array([monty_scalar(1), 0, 0, 0], np.uint32)
-                    for c in range(lde.width):
-                        rys = ef_add(rys, ef_mul(apw, ys[c]))
-                        apw = ef_mul(apw, alpha)
+                    if alpha_pows.shape[0] < lde.width:
+                        alpha_pows = ef_powers(alpha, lde.width)
+                    rys = ef_dot(alpha_pows[:lde.width], ys)          # sum_c alpha^c * p_c(z)
                     apo = ef_pow(alpha, num_reduced[lh])
                     self.reduce_openings(rr, lde.rows, inv, rys, apo, reduced[lh])
                     num_reduced[lh] += lde.width
                     per_mat.append(ys)
-                    keep.append(inv)
                 keep.append(rr)
                 per_round.append(per_mat)
             opened.append(per_round)
@@ -248,7 +250,7 @@ class TwoAdicFriPcs:
         proof = {"alpha": alpha, "commit_phase_commits": res.commits, "betas": res.betas, "final_poly": res.final_poly_coeffs,
                  "pow_witness": pow_witness, "query_indices": indices, "input_openings": input_openings, "commit_phase_openings": cp_openings,
                  "log_max_height": log_max}
-        res._keep = (reduced, keep)
+        res._keep = (reduced, keep, inv_cache)
         proof["_commit_phase"] = res
         return opened, proof
 
