@@ -189,6 +189,7 @@ int b200zk_reduce_openings(b200zk_ctx*, const uint32_t* d_reduced_row, uint64_t 
 int b200zk_dev_alloc(b200zk_ctx*, uint64_t bytes, void** d_out);
 void b200zk_dev_free(b200zk_ctx*, void* d_ptr);
 int b200zk_dev_upload(b200zk_ctx*, void* d_dst, const void* h_src, uint64_t bytes);
+int b200zk_dev_zero(b200zk_ctx*, void* d_dst, uint64_t bytes);   /* cudaMemsetAsync on the ctx stream */
 int b200zk_dev_download(b200zk_ctx*, void* h_dst, const void* d_src, uint64_t bytes);
 
 #ifdef __cplusplus

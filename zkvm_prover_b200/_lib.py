@@ -97,6 +97,7 @@ _SIGS = {
     "b200zk_dev_alloc": (_int, [_p, _u64, C.POINTER(_p)]),
     "b200zk_dev_free": (None, [_p, _p]),
     "b200zk_dev_upload": (_int, [_p, _p, _p, _u64]),
+    "b200zk_dev_zero": (_int, [_p, _p, _u64]),
     "b200zk_dev_download": (_int, [_p, _p, _p, _u64]),
 }
 

@@ -1578,6 +1578,13 @@ int b200zk_dev_alloc(b200zk_ctx* ctx, uint64_t bytes, void** d_out) {
     return dev_alloc(ctx, bytes, d_out);
 }
 void b200zk_dev_free(b200zk_ctx* ctx, void* d) { dev_free(ctx, d); }
+int b200zk_dev_zero(b200zk_ctx* ctx, void* d, uint64_t bytes) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d && bytes) return fail(ctx, B200ZK_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(ctx->device));
+    if (bytes) CU(cudaMemsetAsync(d, 0, bytes, ctx->stream));
+    return B200ZK_OK;
+}
 int b200zk_dev_upload(b200zk_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes) {
     if (!ctx) return B200ZK_ERR_ARG;
     if (!d_dst || !h_src) return fail(ctx, B200ZK_ERR_ARG, "null pointer");

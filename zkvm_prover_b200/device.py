@@ -105,8 +105,7 @@ class DeviceBuffer:
         return b
 
     def zero(self):
-        z = np.zeros(self.nbytes, np.uint8)
-        self.ctx.check(self.ctx.lib.b200zk_dev_upload(self.ctx.h, self.ptr, z.ctypes.data, self.nbytes))
+        self.ctx.check(self.ctx.lib.b200zk_dev_zero(self.ctx.h, self.ptr, self.nbytes))
         return self
 
     def to_host(self, shape, dtype=np.uint32) -> np.ndarray:
@@ -133,16 +132,21 @@ class DeviceMatrix:
     def __init__(self, ctx: Context, handle, owns_handle: bool):
         self.ctx, self.h, self._owns = ctx, handle, owns_handle
         self._keepalive = None
+        self._rows = self._width = None   # a matrix never changes shape: ask the library once
 
     @property
     def rows(self) -> int:
-        return int(self.ctx.lib.b200zk_mat_rows(self.h))
+        if self._rows is None:
+            self._rows = int(self.ctx.lib.b200zk_mat_rows(self.h))
+        return self._rows
 
     height = rows
 
     @property
     def width(self) -> int:
-        return int(self.ctx.lib.b200zk_mat_width(self.h))
+        if self._width is None:
+            self._width = int(self.ctx.lib.b200zk_mat_width(self.h))
+        return self._width
 
     @property
     def device_ptr(self) -> int:

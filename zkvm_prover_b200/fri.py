@@ -9,7 +9,7 @@ import numpy as np
 
 from .challenger import DuplexChallenger
 from .device import Context, DeviceBuffer, DeviceMatrix, default_context
-from .field import GENERATOR_MONTY, P, ef_add, ef_dot, ef_mul, ef_pow, ef_powers, ef_scale_base, monty_scalar, two_adic_generator
+from .field import GENERATOR_MONTY, P, ef_add, ef_dot, ef_mul, ef_pow, ef_powers, ef_scale_base, from_monty, monty_scalar, two_adic_generator
 from .mmcs import DIGEST, MerkleTreeMmcs, ProverData
 
 
@@ -206,7 +206,12 @@ class TwoAdicFriPcs:
          -- the arithmetic of every step is."""
         alpha = challenger.sample_algebra_element()
         reduced, num_reduced, opened, keep = {}, {}, [], []
-        alpha_pows = np.zeros((0, 4), np.uint32)
+        # alpha^0 .. alpha^n with n = the largest running offset any height class reaches
+        per_height = {}
+        for pd, points in rounds:
+            for lde, pts in zip(pd.mats, points):
+                per_height[lde.rows] = per_height.get(lde.rows, 0) + lde.width * len(pts)
+        alpha_pows = ef_powers(alpha, max(per_height.values()) + 1)
         inv_cache = {}
         for pd, points in rounds:
             per_round = []
@@ -223,10 +228,8 @@ class TwoAdicFriPcs:
                         inv_cache[key] = self.inv_denominators(lh, zpt)
                     inv = inv_cache[key]
                     ys = self.interpolate_coset(lde, zpt, inv)
-                    if alpha_pows.shape[0] < lde.width:
-                        alpha_pows = ef_powers(alpha, lde.width)
                     rys = ef_dot(alpha_pows[:lde.width], ys)          # sum_c alpha^c * p_c(z)
-                    apo = ef_pow(alpha, num_reduced[lh])
+                    apo = alpha_pows[num_reduced[lh]]
                     self.reduce_openings(rr, lde.rows, inv, rys, apo, reduced[lh])
                     num_reduced[lh] += lde.width
                     per_mat.append(ys)
@@ -238,7 +241,8 @@ class TwoAdicFriPcs:
         res = commit_phase(self.config, inputs, challenger, self.ctx)
         pow_witness = challenger.grind(self.config.proof_of_work_bits)
         log_max = heights[0]
-        indices = [challenger.sample_bits(log_max) for _ in range(self.config.num_queries)]
+        # sample_bits = canonical value of one sampled element, masked: all query indices in one device round trip
+        indices = [int(v) & ((1 << log_max) - 1) for v in from_monty(challenger.sample_vec(self.config.num_queries))]
         input_openings = []
         for pd, _ in rounds:
             lmh = max(m.rows for m in pd.mats).bit_length() - 1

@@ -83,14 +83,8 @@ class MerkleTreeMmcs:
         rows = np.empty((idx.size, total), np.uint32)
         paths = np.empty((idx.size, depth, DIGEST), np.uint32)
         self.ctx.check(self.ctx.lib.b200zk_merkle_open_many(self.ctx.h, prover_data.h, idx.ctypes.data, idx.size, rows.ctypes.data, paths.ctypes.data))
-        out = []
-        for q in range(idx.size):
-            vals, off = [], 0
-            for m in prover_data.mats:
-                vals.append(rows[q, off:off + m.width].copy())
-                off += m.width
-            out.append((vals, paths[q]))
-        return out
+        bounds = np.cumsum([0] + [m.width for m in prover_data.mats])
+        return [([rows[q, a:b] for a, b in zip(bounds[:-1], bounds[1:])], paths[q]) for q in range(idx.size)]   # views into one buffer
 
     def get_matrices(self, prover_data: ProverData):
         return list(prover_data.mats)
