@@ -181,6 +181,14 @@ int b200zk_mat_dot_ext_powers(b200zk_ctx*, const b200zk_mat*, const uint32_t h_a
  * h_ys[c] = p_c(z) for every column.  d_inv_den: b200zk_open_denominators for (log2(rows), shift, z). */
 int b200zk_interpolate_coset(b200zk_ctx*, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift_monty, const uint32_t h_point[4],
                              const uint32_t* d_inv_den, uint32_t* h_ys /* width x 4 */);
+/* d_out[c] = alpha^c, c < n (EF4) */
+int b200zk_ext_powers(b200zk_ctx*, const uint32_t h_alpha[4], uint32_t n, uint32_t* d_out /* n x 4 */);
+/* one (matrix, point) step of TwoAdicFriPcs::open without a host round trip: opened values into d_ys (width x 4, device),
+ * reduced_ys = sum_c alpha^c * ys[c], then d_ro[i] += alpha^offset * (reduced_ys - d_reduced_row[i]) * d_inv_den[i].
+ * d_alpha_pows: b200zk_ext_powers with n > max(width - 1, alpha_offset); d_reduced_row: b200zk_mat_dot_ext_powers. */
+int b200zk_open_reduce(b200zk_ctx*, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift_monty, const uint32_t h_point[4],
+                       const uint32_t* d_inv_den, const uint32_t* d_reduced_row, const uint32_t* d_alpha_pows, uint32_t alpha_offset,
+                       uint32_t* d_ro /* rows x 4 */, uint32_t* d_ys /* width x 4 */);
 /* d_ro[i] += alpha_pow_offset * (reduced_ys - d_reduced_row[i]) * d_inv_den[i]   (i < m, EF4 everywhere) */
 int b200zk_reduce_openings(b200zk_ctx*, const uint32_t* d_reduced_row, uint64_t m, const uint32_t* d_inv_den, const uint32_t h_reduced_ys[4],
                            const uint32_t h_alpha_pow_offset[4], uint32_t* d_ro);

@@ -395,6 +395,22 @@ def test_open_phase_primitives_match_oracle(z, ctx, n, w, b):
     pcs.reduce_openings(rr, m, inv, rys, apo, ro)
     exp = O.reduce_openings(orr, z.GENERATOR_MONTY, zp, rys, apo, ro0)
     assert np.array_equal(ro.to_host((m, 4)), exp)
+    # the fused device-resident step (b200zk_ext_powers + b200zk_open_reduce): alpha powers, opened values, reduced sum and
+    # the accumulation with alpha^offset, no host round trip -- must equal the pieces checked above
+    off = 3
+    npw = max(w, off + 1)
+    d_pw = z.DeviceBuffer(ctx, 16 * npw)
+    ctx.check(ctx.lib.b200zk_ext_powers(ctx.h, alpha.ctypes.data, npw, d_pw.ptr))
+    pw_full = np.zeros((npw, 4), np.uint32)
+    pw_full[0] = [O.MONTY_ONE, 0, 0, 0]
+    for c in range(1, npw):
+        L.orc_ef_mul(np.ascontiguousarray(pw_full[c - 1]), np.ascontiguousarray(alpha), pw_full[c])
+    assert np.array_equal(d_pw.to_host((npw, 4)), pw_full)
+    d_ys = z.DeviceBuffer(ctx, 16 * w)
+    ro2 = z.DeviceBuffer.from_host(ctx, ro0)
+    ctx.check(ctx.lib.b200zk_open_reduce(ctx.h, lde.h, b, z.GENERATOR_MONTY, zp.ctypes.data, inv.ptr, rr.ptr, d_pw.ptr, off, ro2.ptr, d_ys.ptr))
+    assert np.array_equal(d_ys.to_host((w, 4)), oys)
+    assert np.array_equal(ro2.to_host((m, 4)), O.reduce_openings(orr, z.GENERATOR_MONTY, zp, rys, pw_full[off], ro0))
 
 
 @pytest.mark.parametrize("lf", [0, 2])

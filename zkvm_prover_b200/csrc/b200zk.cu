@@ -1507,10 +1507,11 @@ int b200zk_mat_dot_ext_powers(b200zk_ctx* ctx, const b200zk_mat* m, const uint32
     return B200ZK_OK;
 }
 
-int b200zk_interpolate_coset(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift, const uint32_t h_point[4], const uint32_t* d_inv_den,
-                             uint32_t* h_ys) {
+// opened values of every column into DEVICE memory (d_ys: width x 4); everything is enqueued on the ctx stream
+static int interpolate_coset_dev(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift, const uint32_t h_point[4], const uint32_t* d_inv_den,
+                                 uint32_t* d_ys) {
     TRY(check_mat(ctx, lde));
-    if (!h_point || !d_inv_den || !h_ys) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (!h_point || !d_inv_den || !d_ys) return fail(ctx, B200ZK_ERR_ARG, "null argument");
     if (!is_pow2(lde->rows) || (lde->rows >> log_blowup) == 0) return fail(ctx, B200ZK_ERR_SHAPE, "bad LDE height / blow-up");
     if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
     CU(cudaSetDevice(ctx->device));
@@ -1536,9 +1537,8 @@ int b200zk_interpolate_coset(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t lo
     uint32_t row_blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, ((uint64_t)ctx->num_sms * 4 + col_blocks - 1) / col_blocks));
     const uint32_t rows_per_cta = (uint32_t)(((n + row_blocks - 1) / row_blocks + 63) / 64 * 64);
     row_blocks = (uint32_t)((n + rows_per_cta - 1) / rows_per_cta);
-    uint32_t *d_partial = nullptr, *d_ys = nullptr;
+    uint32_t* d_partial = nullptr;
     TRY(dev_alloc(ctx, (size_t)row_blocks * W * 16, (void**)&d_partial));
-    TRY(dev_alloc(ctx, (size_t)W * 16, (void**)&d_ys));
     dim3 grid(row_blocks, col_blocks);
     const size_t rsm = (size_t)256 * vecw * 16;  // [ty][tx * VEC][4] words
     if (vec4) op::colwise_bary_kernel<4><<<grid, 256, rsm, ctx->stream>>>(lde->d, n, W, lm, shift, ctx->tw_lo[lm], ctx->tw_hi[lm], d_inv_den, rows_per_cta, tx_n, d_partial);
@@ -1546,10 +1546,53 @@ int b200zk_interpolate_coset(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t lo
     LAUNCHED();
     op::bary_finish_kernel<<<(W + 127) / 128, 128, 0, ctx->stream>>>(d_partial, row_blocks, W, d_scale, d_ys);
     LAUNCHED();
-    CU(cudaMemcpyAsync(h_ys, d_ys, (size_t)W * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
     dev_free(ctx, d_partial);
+    return B200ZK_OK;
+}
+
+
+int b200zk_interpolate_coset(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift, const uint32_t h_point[4], const uint32_t* d_inv_den,
+                             uint32_t* h_ys) {
+    TRY(check_mat(ctx, lde));
+    if (!h_ys) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    uint32_t* d_ys = nullptr;
+    TRY(dev_alloc(ctx, (size_t)lde->width * 16, (void**)&d_ys));
+    int rc = interpolate_coset_dev(ctx, lde, log_blowup, shift, h_point, d_inv_den, d_ys);
+    if (rc == B200ZK_OK) {
+        cudaError_t e = cudaMemcpyAsync(h_ys, d_ys, (size_t)lde->width * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    }
     dev_free(ctx, d_ys);
+    return rc;
+}
+
+int b200zk_ext_powers(b200zk_ctx* ctx, const uint32_t h_alpha[4], uint32_t n, uint32_t* d_out) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!h_alpha || (!d_out && n)) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (!n) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d_alpha = nullptr;
+    TRY(dev_alloc(ctx, 16, (void**)&d_alpha));
+    CU(cudaMemcpyAsync(d_alpha, h_alpha, 16, cudaMemcpyHostToDevice, ctx->stream));
+    op::ext_powers_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_alpha, n, d_out);
+    LAUNCHED();
+    dev_free(ctx, d_alpha);
+    return B200ZK_OK;
+}
+
+int b200zk_open_reduce(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_t log_blowup, uint32_t shift, const uint32_t h_point[4], const uint32_t* d_inv_den,
+                       const uint32_t* d_reduced_row, const uint32_t* d_alpha_pows, uint32_t alpha_offset, uint32_t* d_ro, uint32_t* d_ys) {
+    TRY(check_mat(ctx, lde));
+    if (!d_reduced_row || !d_alpha_pows || !d_ro) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    TRY(interpolate_coset_dev(ctx, lde, log_blowup, shift, h_point, d_inv_den, d_ys));
+    uint32_t* d_c = nullptr;
+    TRY(dev_alloc(ctx, 32, (void**)&d_c));
+    op::ef_dot_kernel<<<1, 256, 0, ctx->stream>>>(d_alpha_pows, d_ys, lde->width, alpha_offset, d_c);
+    LAUNCHED();
+    op::reduce_openings_kernel<<<(uint32_t)((lde->rows + 255) / 256), 256, 0, ctx->stream>>>(d_reduced_row, lde->rows, d_inv_den, d_c, d_c + 4, d_ro);
+    LAUNCHED();
+    dev_free(ctx, d_c);
     return B200ZK_OK;
 }
 

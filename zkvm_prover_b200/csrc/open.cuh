@@ -271,4 +271,23 @@ __global__ void __launch_bounds__(256) reduce_openings_kernel(const uint32_t* __
     ef_store(ro + 4 * i, bb::ef_add(ef_load(ro + 4 * i), t));
 }
 
+// out[0..4) = sum_c pw[c] * ys[c] (the reduced opening sum_c alpha^c p_c(z)), out[4..8) = pw[offset] (alpha^offset);
+// one CTA, the two constants reduce_openings_kernel needs, produced without leaving the device
+__global__ void __launch_bounds__(256) ef_dot_kernel(const uint32_t* __restrict__ pw, const uint32_t* __restrict__ ys, uint32_t width, uint32_t offset,
+                                                     uint32_t* __restrict__ out) {
+    __shared__ uint32_t part[256 * 4];
+    ef4 acc{{0, 0, 0, 0}};
+    for (uint32_t c = threadIdx.x; c < width; c += 256) acc = bb::ef_add(acc, bb::ef_mul(ef_load(pw + 4 * c), ef_load(ys + 4 * c)));
+    ef_store(part + 4 * threadIdx.x, acc);
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) ef_store(part + 4 * threadIdx.x, bb::ef_add(ef_load(part + 4 * threadIdx.x), ef_load(part + 4 * (threadIdx.x + s))));
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) {
+        out[threadIdx.x] = part[threadIdx.x];
+        out[4 + threadIdx.x] = pw[4 * (size_t)offset + threadIdx.x];
+    }
+}
+
 }  // namespace op

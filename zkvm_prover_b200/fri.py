@@ -205,14 +205,19 @@ class TwoAdicFriPcs:
         of transcript operations is restated from memory of that crate and is NOT pinned by a reference vector
          -- the arithmetic of every step is."""
         alpha = challenger.sample_algebra_element()
-        reduced, num_reduced, opened, keep = {}, {}, [], []
-        # alpha^0 .. alpha^n with n = the largest running offset any height class reaches
-        per_height = {}
+        reduced, num_reduced, keep = {}, {}, []
+        # alpha^0 .. alpha^n on the device, n = the largest running offset any height class reaches
+        per_height, total_cols = {}, 0
         for pd, points in rounds:
             for lde, pts in zip(pd.mats, points):
                 per_height[lde.rows] = per_height.get(lde.rows, 0) + lde.width * len(pts)
-        alpha_pows = ef_powers(alpha, max(per_height.values()) + 1)
-        inv_cache = {}
+                total_cols += lde.width * len(pts)
+        n_pows = max(per_height.values()) + 1
+        a4 = np.ascontiguousarray(alpha, dtype=np.uint32)
+        alpha_pows = DeviceBuffer(self.ctx, 16 * n_pows)
+        self.ctx.check(self.ctx.lib.b200zk_ext_powers(self.ctx.h, a4.ctypes.data, n_pows, alpha_pows.ptr))
+        ys_all = DeviceBuffer(self.ctx, 16 * total_cols)   # every opened value, downloaded once at the end
+        inv_cache, slots, off = {}, [], 0
         for pd, points in rounds:
             per_round = []
             for lde, pts in zip(pd.mats, points):
@@ -223,19 +228,20 @@ class TwoAdicFriPcs:
                 rr = self.dot_ext_powers(lde, alpha)
                 per_mat = []
                 for zpt in pts:
-                    key = (lh, np.asarray(zpt, np.uint32).tobytes())
+                    z4 = np.ascontiguousarray(zpt, dtype=np.uint32)
+                    key = (lh, z4.tobytes())
                     if key not in inv_cache:               # matrices of one height share 1 / (z - x) for a common point
                         inv_cache[key] = self.inv_denominators(lh, zpt)
-                    inv = inv_cache[key]
-                    ys = self.interpolate_coset(lde, zpt, inv)
-                    rys = ef_dot(alpha_pows[:lde.width], ys)          # sum_c alpha^c * p_c(z)
-                    apo = alpha_pows[num_reduced[lh]]
-                    self.reduce_openings(rr, lde.rows, inv, rys, apo, reduced[lh])
+                    # opened values -> reduced opening -> accumulate into the height's FRI input, all on the device
+                    self.ctx.check(self.ctx.lib.b200zk_open_reduce(self.ctx.h, lde.h, self.config.log_blowup, GENERATOR_MONTY, z4.ctypes.data,
+                                                                   inv_cache[key].ptr, rr.ptr, alpha_pows.ptr, num_reduced[lh], reduced[lh].ptr,
+                                                                   ys_all.ptr + 16 * off))
                     num_reduced[lh] += lde.width
-                    per_mat.append(ys)
+                    per_mat.append((off, lde.width))
+                    off += lde.width
                 keep.append(rr)
                 per_round.append(per_mat)
-            opened.append(per_round)
+            slots.append(per_round)
         heights = sorted(reduced, reverse=True)
         inputs = [(reduced[lh].ptr, 1 << lh) for lh in heights]
         res = commit_phase(self.config, inputs, challenger, self.ctx)
@@ -254,7 +260,9 @@ class TwoAdicFriPcs:
         proof = {"alpha": alpha, "commit_phase_commits": res.commits, "betas": res.betas, "final_poly": res.final_poly_coeffs,
                  "pow_witness": pow_witness, "query_indices": indices, "input_openings": input_openings, "commit_phase_openings": cp_openings,
                  "log_max_height": log_max}
-        res._keep = (reduced, keep, inv_cache)
+        ys_host = ys_all.to_host((total_cols, 4))
+        opened = [[[ys_host[o:o + w] for o, w in per_mat] for per_mat in per_round] for per_round in slots]
+        res._keep = (reduced, keep, inv_cache, alpha_pows, ys_all)
         proof["_commit_phase"] = res
         return opened, proof
 
