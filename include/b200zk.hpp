@@ -7,12 +7,15 @@
 //                                                                      -> Poseidon2BabyBear16 / PaddingFreeSponge / TruncatedPermutation
 //   p3_commit::Mmcs (p3_merkle_tree::MerkleTreeMmcs<.., 8>)             -> MerkleTreeMmcs
 //   p3_challenger::DuplexChallenger<BabyBear, Perm, 16, 8>              -> DuplexChallenger
-//   p3_fri::prover::commit_phase / TwoAdicFriPcs::commit                -> commit_phase / TwoAdicFriPcs
+//   p3_fri::prover::commit_phase / TwoAdicFriPcs::{commit, open}        -> commit_phase / TwoAdicFriPcs (+ FriProof with its bincode encoding)
 // Provers are infallible in Plonky3 (they panic on misuse); here misuse throws b200zk::Error carrying the ABI code.
 // Field elements are Montgomery-form uint32_t, matrices row-major.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <cstring>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -85,6 +88,46 @@ class DeviceMatrix {
     b200zk_mat* m_ = nullptr;
     bool owns_ = true;
 };
+
+// raw device allocation from the library's pool (EF4 vectors of the open phase)
+class DeviceBuffer {
+   public:
+    DeviceBuffer(const Context& c, uint64_t bytes) : c_(&c), bytes_(bytes) { c.check(b200zk_dev_alloc(c.raw(), bytes, &p_)); }
+    DeviceBuffer(DeviceBuffer&& o) noexcept : c_(o.c_), p_(o.p_), bytes_(o.bytes_) { o.p_ = nullptr; }
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    ~DeviceBuffer() {
+        if (p_) b200zk_dev_free(c_->raw(), p_);
+    }
+    uint32_t* ptr() const { return static_cast<uint32_t*>(p_); }
+    uint64_t bytes() const { return bytes_; }
+    void zero() const { c_->check(b200zk_dev_zero(c_->raw(), p_, bytes_)); }
+    void download(void* host, uint64_t bytes) const { c_->check(b200zk_dev_download(c_->raw(), host, p_, bytes)); }
+
+   private:
+    const Context* c_;
+    void* p_ = nullptr;
+    uint64_t bytes_ = 0;
+};
+
+// ---- host-side field glue (a handful of elements per proof)
+namespace field {
+constexpr uint64_t P = B200ZK_P;
+constexpr uint64_t RINV = 943718400u;  // 2^-32 mod p
+inline F from_monty(F m) { return (F)((unsigned __int128)m * RINV % P); }
+inline F to_monty(uint64_t x) { return (F)(((x % P) << 32) % P); }
+inline F mul(F a, F b) { return (F)((unsigned __int128)a * b % P * RINV % P); }  // Montgomery product
+inline uint64_t powmod(uint64_t b, uint64_t e) {
+    uint64_t r = 1;
+    for (b %= P; e; e >>= 1, b = b * b % P)
+        if (e & 1) r = r * b % P;
+    return r;
+}
+// BabyBear::two_adic_generator(bits), Montgomery form (31^15 generates the 2^27 subgroup)
+inline F two_adic_generator(uint32_t bits) {
+    if (bits > 27) throw Error(B200ZK_ERR_ARG, "BabyBear has two-adicity 27");
+    return to_monty(powmod(powmod(31, 15), 1ull << (27 - bits)));
+}
+}  // namespace field
 
 // ---- p3_dft::TwoAdicSubgroupDft
 class B200Dft {
@@ -228,6 +271,28 @@ class MerkleTreeMmcs {
         }
         return o;
     }
+    // the query phase's loop over open_batch, one launch and one download
+    std::vector<BatchOpening> open_batch_many(const std::vector<uint64_t>& indices, const ProverData& d) const {
+        const size_t total = b200zk_tree_total_width(d.raw()), depth = d.depth(), nq = indices.size();
+        std::vector<F> rows(total * nq), paths(8 * depth * nq);
+        c_->check(b200zk_merkle_open_many(c_->raw(), d.raw(), indices.data(), (uint32_t)nq, rows.data(), paths.data()));
+        std::vector<uint32_t> widths;
+        for (uint32_t i = 0; i < d.num_matrices(); i++) widths.push_back(b200zk_mat_width(b200zk_tree_mat(d.raw(), i)));
+        std::vector<BatchOpening> out(nq);
+        for (size_t q = 0; q < nq; q++) {
+            size_t off = q * total;
+            for (uint32_t w : widths) {
+                out[q].opened_values.emplace_back(rows.begin() + off, rows.begin() + off + w);
+                off += w;
+            }
+            for (size_t l = 0; l < depth; l++) {
+                Digest dg;
+                for (int j = 0; j < 8; j++) dg[j] = paths[(q * depth + l) * 8 + j];
+                out[q].opening_proof.push_back(dg);
+            }
+        }
+        return out;
+    }
     std::vector<DeviceMatrix> get_matrices(const ProverData& d) const {
         std::vector<DeviceMatrix> v;
         for (uint32_t i = 0; i < d.num_matrices(); i++) v.push_back(d.matrix(i));
@@ -271,6 +336,11 @@ class DuplexChallenger {
         c_->check(b200zk_chal_sample(c_->raw(), h_, &v, 1));
         return v;
     }
+    std::vector<F> sample_vec(uint32_t n) {
+        std::vector<F> v(n);
+        if (n) c_->check(b200zk_chal_sample(c_->raw(), h_, v.data(), n));
+        return v;
+    }
     EF4 sample_algebra_element() {
         EF4 e;
         c_->check(b200zk_chal_sample(c_->raw(), h_, e.data(), 4));
@@ -305,6 +375,7 @@ struct CommitPhaseResult {
     std::vector<ProverData> data;
     std::vector<EF4> final_poly_evals;  // last folded vector, bit-reversed order
     std::vector<EF4> betas;
+    std::vector<EF4> final_poly;        // its coefficients (un-bit-reversed, idft_algebra, truncated to final_poly_len), observed
 };
 // prover::commit_phase for device-resident inputs (EF4 vectors, bit-reversed, strictly decreasing lengths)
 inline CommitPhaseResult commit_phase(const Context& c, const FriConfig& cfg, const std::vector<std::pair<const uint32_t*, uint64_t>>& d_inputs,
@@ -334,8 +405,64 @@ inline CommitPhaseResult commit_phase(const Context& c, const FriConfig& cfg, co
         r.data.emplace_back(c, trees[i]);
     }
     for (size_t i = 0; i < fin.size() / 4; i++) r.final_poly_evals.push_back({fin[4 * i], fin[4 * i + 1], fin[4 * i + 2], fin[4 * i + 3]});
+    // p3-fri tail: reverse_slice_index_bits, idft_algebra (each of the 4 basis coordinates is a column), keep final_poly_len
+    // coefficients and let the challenger observe them
+    const uint32_t lb = cfg.log_blowup + cfg.log_final_poly_len;
+    const size_t stop = (size_t)1 << lb;
+    std::vector<F> nat(4 * stop);
+    for (size_t i = 0; i < stop; i++) {
+        size_t j = 0;
+        for (uint32_t b = 0; b < lb; b++) j |= ((i >> b) & 1) << (lb - 1 - b);
+        for (int k = 0; k < 4; k++) nat[4 * i + k] = fin[4 * j + k];
+    }
+    std::vector<F> coef = B200Dft(c).idft_batch(DeviceMatrix(c, nat, stop, 4)).to_row_major_matrix();
+    std::vector<F> obs;
+    for (size_t i = 0; i < ((size_t)1 << cfg.log_final_poly_len); i++) {
+        r.final_poly.push_back({coef[4 * i], coef[4 * i + 1], coef[4 * i + 2], coef[4 * i + 3]});
+        obs.insert(obs.end(), coef.begin() + 4 * i, coef.begin() + 4 * i + 4);
+    }
+    challenger.observe_slice(obs);
     return r;
 }
+
+// ---- p3_fri proof types and their wire encoding (bincode v1, the reference's legacy proof format: lengths as u64,
+// fixed-size arrays without a length, little-endian u32 Montgomery words; crates/types/src/proof.rs:70-74)
+struct CommitPhaseProofStep {
+    EF4 sibling_value;
+    std::vector<Digest> opening_proof;
+};
+struct QueryProof {
+    std::vector<BatchOpening> input_proof;                    // one per committed round
+    std::vector<CommitPhaseProofStep> commit_phase_openings;  // one per FRI round
+};
+struct FriProof {
+    std::vector<Digest> commit_phase_commits;
+    std::vector<QueryProof> query_proofs;
+    std::vector<EF4> final_poly;
+    F pow_witness = 0;
+    std::vector<uint8_t> encode() const {
+        std::vector<uint8_t> out;
+        auto u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i))); };
+        auto u32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) out.push_back((uint8_t)(v >> (8 * i))); };
+        auto digests = [&](const std::vector<Digest>& v) { u64(v.size()); for (auto& d : v) for (F x : d) u32(x); };
+        digests(commit_phase_commits);
+        u64(query_proofs.size());
+        for (auto& q : query_proofs) {
+            u64(q.input_proof.size());
+            for (auto& b : q.input_proof) {
+                u64(b.opened_values.size());
+                for (auto& row : b.opened_values) { u64(row.size()); for (F x : row) u32(x); }
+                digests(b.opening_proof);
+            }
+            u64(q.commit_phase_openings.size());
+            for (auto& st : q.commit_phase_openings) { for (F x : st.sibling_value) u32(x); digests(st.opening_proof); }
+        }
+        u64(final_poly.size());
+        for (auto& e : final_poly) for (F x : e) u32(x);
+        u32(pow_witness);
+        return out;
+    }
+};
 
 // the commit half of TwoAdicFriPcs: LDE every trace (shift = GENERATOR / domain shift), bit-reversed rows, one MMCS commit
 class TwoAdicFriPcs {
@@ -354,7 +481,117 @@ class TwoAdicFriPcs {
         return {root, ProverData(*c_, t)};
     }
 
+    // The prover side of TwoAdicFriPcs::open with every data-parallel step on the device: per (matrix, point)
+    // opened values + reduced opening accumulated into the per-height FRI input (b200zk_open_reduce), then commit phase, PoW
+    // grinding and the query openings.  points[i]: opening points of matrix i of that commitment.
+    // Returns opened[round][matrix][point][column] and the FriProof.  Same composition as the Python mirror (fri.py).
+    struct OpenRound {
+        const ProverData* data;
+        std::vector<std::vector<EF4>> points;
+    };
+    using OpenedValues = std::vector<std::vector<std::vector<std::vector<EF4>>>>;
+    std::pair<OpenedValues, FriProof> open(const std::vector<OpenRound>& rounds, DuplexChallenger& ch) const {
+        const Context& c = *c_;
+        const EF4 alpha = ch.sample_algebra_element();
+        std::map<uint32_t, uint64_t> per_height;  // log2(height) -> columns x points
+        uint64_t total_cols = 0;
+        for (auto& r : rounds)
+            for (uint32_t i = 0; i < r.data->num_matrices(); i++) {
+                DeviceMatrix m = r.data->matrix(i);
+                per_height[log2u(m.height())] += (uint64_t)m.width() * r.points.at(i).size();
+                total_cols += (uint64_t)m.width() * r.points[i].size();
+            }
+        uint64_t n_pows = 1;
+        for (auto& kv : per_height) n_pows = std::max(n_pows, kv.second + 1);
+        DeviceBuffer alpha_pows(c, 16 * n_pows), ys_all(c, 16 * std::max<uint64_t>(total_cols, 1));
+        c.check(b200zk_ext_powers(c.raw(), alpha.data(), (uint32_t)n_pows, alpha_pows.ptr()));
+        std::map<uint32_t, DeviceBuffer, std::greater<uint32_t>> reduced;   // tallest first
+        std::map<uint32_t, uint32_t> num_reduced;
+        std::map<std::pair<uint32_t, EF4>, DeviceBuffer> inv_cache;
+        std::vector<DeviceBuffer> keep;
+        uint64_t off = 0;
+        for (auto& r : rounds)
+            for (uint32_t i = 0; i < r.data->num_matrices(); i++) {
+                DeviceMatrix lde = r.data->matrix(i);
+                const uint32_t lh = log2u(lde.height());
+                if (!reduced.count(lh)) {
+                    reduced.emplace(lh, DeviceBuffer(c, 16 * lde.height())).first->second.zero();
+                    num_reduced[lh] = 0;
+                }
+                keep.emplace_back(c, 16 * lde.height());
+                const DeviceBuffer& rr = keep.back();
+                c.check(b200zk_mat_dot_ext_powers(c.raw(), lde.raw(), alpha.data(), rr.ptr()));
+                for (const EF4& z : r.points[i]) {
+                    auto key = std::make_pair(lh, z);
+                    auto it = inv_cache.find(key);
+                    if (it == inv_cache.end()) {  // matrices of one height share 1 / (z - x) for a common point
+                        it = inv_cache.emplace(key, DeviceBuffer(c, 16ull << lh)).first;
+                        c.check(b200zk_open_denominators(c.raw(), lh, GENERATOR_MONTY, z.data(), it->second.ptr()));
+                    }
+                    c.check(b200zk_open_reduce(c.raw(), lde.raw(), cfg_.log_blowup, GENERATOR_MONTY, z.data(), it->second.ptr(), rr.ptr(), alpha_pows.ptr(),
+                                               num_reduced[lh], reduced.at(lh).ptr(), ys_all.ptr() + 4 * off));
+                    num_reduced[lh] += lde.width();
+                    off += lde.width();
+                }
+            }
+        std::vector<std::pair<const uint32_t*, uint64_t>> inputs;
+        for (auto& kv : reduced) inputs.push_back({kv.second.ptr(), 1ull << kv.first});
+        CommitPhaseResult res = commit_phase(c, cfg_, inputs, ch);
+        FriProof proof;
+        proof.commit_phase_commits = res.commits;
+        proof.final_poly = res.final_poly;
+        proof.pow_witness = ch.grind(cfg_.proof_of_work_bits);
+        const uint32_t log_max = reduced.begin()->first;
+        std::vector<uint64_t> indices;  // sample_bits = canonical value of one sampled element, masked
+        for (F v : ch.sample_vec(cfg_.num_queries)) indices.push_back(field::from_monty(v) & ((1ull << log_max) - 1));
+        proof.query_proofs.resize(indices.size());
+        for (auto& r : rounds) {
+            uint64_t max_h = 0;
+            for (uint32_t i = 0; i < r.data->num_matrices(); i++) max_h = std::max(max_h, r.data->matrix(i).height());
+            std::vector<uint64_t> idx;
+            for (uint64_t q : indices) idx.push_back(q >> (log_max - log2u(max_h)));
+            auto opens = MerkleTreeMmcs(c).open_batch_many(idx, *r.data);
+            for (size_t q = 0; q < indices.size(); q++) proof.query_proofs[q].input_proof.push_back(std::move(opens[q]));
+        }
+        for (size_t rd = 0; rd < res.data.size(); rd++) {
+            std::vector<uint64_t> idx;
+            for (uint64_t q : indices) idx.push_back((q >> rd) >> 1);
+            auto opens = MerkleTreeMmcs(c).open_batch_many(idx, res.data[rd]);
+            for (size_t q = 0; q < indices.size(); q++) {
+                const std::vector<F>& pair = opens[q].opened_values.at(0);  // (lo, hi) of the queried pair, 8 words
+                const size_t sib = 1 - ((indices[q] >> rd) & 1);             // the proof carries the OTHER value
+                CommitPhaseProofStep st;
+                for (int k = 0; k < 4; k++) st.sibling_value[k] = pair[4 * sib + k];
+                st.opening_proof = std::move(opens[q].opening_proof);
+                proof.query_proofs[q].commit_phase_openings.push_back(std::move(st));
+            }
+        }
+        std::vector<F> ys(4 * total_cols);
+        if (total_cols) ys_all.download(ys.data(), 16 * total_cols);
+        OpenedValues opened;
+        off = 0;
+        for (auto& r : rounds) {
+            opened.emplace_back();
+            for (uint32_t i = 0; i < r.data->num_matrices(); i++) {
+                opened.back().emplace_back();
+                const uint32_t w = r.data->matrix(i).width();
+                for (size_t k = 0; k < r.points[i].size(); k++) {
+                    std::vector<EF4> v(w);
+                    for (uint32_t col = 0; col < w; col++) std::memcpy(v[col].data(), &ys[4 * (off + col)], 16);
+                    opened.back().back().push_back(std::move(v));
+                    off += w;
+                }
+            }
+        }
+        return {std::move(opened), std::move(proof)};
+    }
+
    private:
+    static uint32_t log2u(uint64_t v) {
+        uint32_t l = 0;
+        while ((1ull << l) < v) l++;
+        return l;
+    }
     const Context* c_;
     FriConfig cfg_;
 };

@@ -7,7 +7,49 @@ using namespace b200zk;
 #define REQUIRE(c) do { if (!(c)) { std::printf("FAILED: %s (line %d)\n", #c, __LINE__); return 1; } } while (0)
 static uint32_t to_monty(uint64_t x) { return (uint32_t)(((x % B200ZK_P) << 32) % B200ZK_P); }
 static uint32_t from_monty(uint32_t m) { unsigned __int128 r = (unsigned __int128)m * 943718400u; return (uint32_t)(r % B200ZK_P); }  // 2^-32 mod p
-int main() {
+// deterministic commit -> open through the C++ mirror; the FriProof bytes and the opened values go to files so that
+// tests/test_gpu_cpp_mirror.py can compare them with the Python mirror's (whose proof an independent verifier accepts)
+static int open_flow(const char* proof_path, const char* opened_path) {
+    Context ctx(0);
+    FriConfig cfg;
+    cfg.log_blowup = 1; cfg.log_final_poly_len = 0; cfg.num_queries = 5; cfg.proof_of_work_bits = 6;
+    TwoAdicFriPcs pcs(ctx, cfg);
+    auto gen = [&](uint64_t n, uint32_t w, uint64_t seed) {
+        std::vector<F> v(n * w);
+        for (size_t i = 0; i < v.size(); i++) v[i] = to_monty(i * 2654435761ull + 17 + seed);
+        return DeviceMatrix(ctx, v, n, w);
+    };
+    DeviceMatrix a = gen(1 << 9, 12, 1), b = gen(1 << 7, 5, 2), c3 = gen(1 << 9, 3, 3);
+    auto [root1, pd1] = pcs.commit({&a, &b});
+    auto [root2, pd2] = pcs.commit({&c3});
+    DuplexChallenger ch(ctx);
+    ch.observe(root1);
+    ch.observe(root2);
+    const EF4 zeta = ch.sample_algebra_element();
+    auto pts = [&](uint32_t log_n) {
+        const F g = field::two_adic_generator(log_n);
+        EF4 zg;
+        for (int k = 0; k < 4; k++) zg[k] = field::mul(zeta[k], g);
+        return std::vector<EF4>{zeta, zg};
+    };
+    std::vector<TwoAdicFriPcs::OpenRound> rounds = {{&pd1, {pts(9), pts(7)}}, {&pd2, {pts(9)}}};
+    auto [opened, proof] = pcs.open(rounds, ch);
+    REQUIRE(proof.query_proofs.size() == 5 && proof.commit_phase_commits.size() == 9 && proof.final_poly.size() == 1);
+    REQUIRE(opened.size() == 2 && opened[0].size() == 2 && opened[0][0].size() == 2 && opened[0][0][0].size() == 12);
+    std::vector<uint8_t> bytes = proof.encode();
+    FILE* fp = std::fopen(proof_path, "wb");
+    REQUIRE(fp && std::fwrite(bytes.data(), 1, bytes.size(), fp) == bytes.size());
+    std::fclose(fp);
+    fp = std::fopen(opened_path, "wb");
+    REQUIRE(fp);
+    for (auto& r : opened) for (auto& m : r) for (auto& p : m) for (auto& e : p) std::fwrite(e.data(), 4, 4, fp);
+    std::fclose(fp);
+    std::printf("cpp open ok, %zu proof bytes\n", bytes.size());
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc == 3) return open_flow(argv[1], argv[2]);
     Context ctx(0);
     Poseidon2BabyBear16 perm(ctx);
     std::array<F, 16> s;
