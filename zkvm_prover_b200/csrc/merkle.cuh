@@ -108,7 +108,7 @@ __device__ __forceinline__ void sponge_rows(const Group& g, uint64_t row, uint32
     }
     // general path (ragged widths, several matrices in one sponge -- the shape of real traces): a cursor walks the
     // concatenated row; 8 elements are gathered with independent loads (selects only where a chunk straddles two
-    // matrices) and the next 8 are already in flight while the permutation runs.
+    // matrices).
     Cursor cur;
     cur.m = 0;
     cur.c = 0;
@@ -124,12 +124,8 @@ __device__ __forceinline__ void sponge_rows(const Group& g, uint64_t row, uint32
 #pragma unroll
             for (int i = 0; i < 8; i++) st[i] = (i < cnt) ? buf[i] : st[i];
         }
-        uint32_t nb[8];
-        const int ncnt = gather8(g, row, cur, nb);
         p2::permute(st);
-#pragma unroll
-        for (int i = 0; i < 8; i++) buf[i] = nb[i];
-        cnt = ncnt;
+        cnt = gather8(g, row, cur, buf);   // loaded at the point of use (prefetching before the permutation measured the same)
     }
 }
 
