@@ -1500,7 +1500,12 @@ int b200zk_mat_dot_ext_powers(b200zk_ctx* ctx, const b200zk_mat* m, const uint32
     const size_t smem = (size_t)((m->width + 3) / 4 * 4) * 16;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((m->rows + 8 * op::DEP_ROWS - 1) / (8 * op::DEP_ROWS), (uint64_t)ctx->num_sms * 8);
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, B200ZK_ERR_SHAPE, "matrix too wide for dot_ext_powers");
-    if (vec4) op::dot_ext_powers_kernel<4><<<grid, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
+    const uint32_t lanes_needed = vec4 ? m->width / 4 : m->width;   // lanes a row keeps busy in the warp-per-row kernel
+    if (lanes_needed <= 24) {  // narrow: one thread per row
+        const uint32_t nblk = (uint32_t)((m->rows + 255) / 256);
+        if (vec4) op::dot_ext_powers_narrow_kernel<4><<<nblk, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
+        else op::dot_ext_powers_narrow_kernel<1><<<nblk, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
+    } else if (vec4) op::dot_ext_powers_kernel<4><<<grid, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
     else op::dot_ext_powers_kernel<1><<<grid, 256, smem, ctx->stream>>>(m->d, m->rows, m->width, d_pw, d_out);
     LAUNCHED();
     dev_free(ctx, d_pw);
@@ -1531,7 +1536,7 @@ static int interpolate_coset_dev(b200zk_ctx* ctx, const b200zk_mat* lde, uint32_
     CU(cudaMemcpyAsync(d_scale, sc.c, 16, cudaMemcpyHostToDevice, ctx->stream));
     const bool vec4 = W % 4 == 0 && ((uintptr_t)lde->d % 16) == 0;
     const uint32_t vecw = vec4 ? 4 : 1;
-    uint32_t tx_n = 32;  // threads along the columns: enough to cover the width, at most the whole CTA
+    uint32_t tx_n = 1;  // threads along the columns: just enough to cover the width (narrow traces leave the rest of the CTA to the rows)
     while (tx_n < 256 && tx_n * vecw < W) tx_n <<= 1;
     const uint32_t col_blocks = (W + tx_n * vecw - 1) / (tx_n * vecw);
     uint32_t row_blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, ((uint64_t)ctx->num_sms * 4 + col_blocks - 1) / col_blocks));

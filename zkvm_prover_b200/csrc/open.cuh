@@ -183,6 +183,51 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t* __r
 // A CTA is TX x TY threads: tx sits on VEC adjacent columns (coalesced rows), ty strides over the rows of the CTA's
 // slab, so narrow matrices still fill the CTA; products of two rows accumulate lazily in 64 bits per reduction.
 // Partial sums of the TY row lanes are combined in shared memory; a second kernel adds the per-CTA partials.
+// The same for narrow matrices (real traces: a dozen columns): one thread per row, so no lane idles beside a short row.
+// Rows are adjacent in memory, a warp's loads cover one contiguous span, and every lane reads the same power entry
+// (shared-memory broadcast).
+template <int VEC>
+__global__ void __launch_bounds__(256) dot_ext_powers_narrow_kernel(const uint32_t* __restrict__ mat, uint64_t rows, uint32_t width,
+                                                                    const uint32_t* __restrict__ pw_g, uint32_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t pw[];  // width x 4, natural order
+    for (uint32_t i = threadIdx.x; i < width; i += blockDim.x) *reinterpret_cast<uint4*>(pw + 4 * i) = *reinterpret_cast<const uint4*>(pw_g + 4 * i);
+    __syncthreads();
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const uint32_t* row = mat + r * width;
+    uint32_t acc[4] = {0, 0, 0, 0};
+    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    uint32_t pending = 0;
+    for (uint32_t c = 0; c < width; c += VEC) {
+        uint32_t v[VEC];
+        if (VEC == 4) {
+            const uint4 t = *reinterpret_cast<const uint4*>(row + c);
+            v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+        } else {
+            v[0] = row[c];
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+            const uint4 pe = *reinterpret_cast<const uint4*>(pw + 4 * (c + e));
+            s0 += (uint64_t)pe.x * v[e];
+            s1 += (uint64_t)pe.y * v[e];
+            s2 += (uint64_t)pe.z * v[e];
+            s3 += (uint64_t)pe.w * v[e];
+            if (++pending == 2) {  // two products per reduction keep the sum below 2^32 * p
+                acc[0] = bb::add(acc[0], reduce2(s0)); acc[1] = bb::add(acc[1], reduce2(s1));
+                acc[2] = bb::add(acc[2], reduce2(s2)); acc[3] = bb::add(acc[3], reduce2(s3));
+                s0 = s1 = s2 = s3 = 0;
+                pending = 0;
+            }
+        }
+    }
+    if (pending) {
+        acc[0] = bb::add(acc[0], reduce2(s0)); acc[1] = bb::add(acc[1], reduce2(s1));
+        acc[2] = bb::add(acc[2], reduce2(s2)); acc[3] = bb::add(acc[3], reduce2(s3));
+    }
+    *reinterpret_cast<uint4*>(out + 4 * r) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) colwise_bary_kernel(const uint32_t* __restrict__ mat, uint64_t n, uint32_t width, int lm, uint32_t shift,
                                                            const uint32_t* __restrict__ tw_lo, const uint32_t* __restrict__ tw_hi,
