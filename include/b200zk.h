@@ -125,6 +125,10 @@ int b200zk_lde_commit_host(b200zk_ctx*, const uint32_t* h_values, uint64_t rows,
 int b200zk_merkle_open(b200zk_ctx*, const b200zk_tree*, uint64_t index, uint32_t* h_rows, uint32_t* h_path);
 /* query phase: the same for n_idx indices in one launch + one copy.  h_rows: n_idx x total_width, h_paths: n_idx x depth x 8 */
 int b200zk_merkle_open_many(b200zk_ctx*, const b200zk_tree*, const uint64_t* h_indices, uint32_t n_idx, uint32_t* h_rows, uint32_t* h_paths);
+/* the query phase over all FRI commit-phase trees (b200zk_fri_commit_phase `trees`): tree r is opened at (index >> r) >> 1 for every
+ * query index; h_pairs: n_trees x n_idx x 8 (the (lo, hi) EF4 pair), h_paths: tree after tree, n_idx x depth_r x 8 */
+int b200zk_fri_open_queries(b200zk_ctx*, const b200zk_tree* const* trees, uint32_t n_trees, const uint64_t* h_indices, uint32_t n_idx,
+                            uint32_t* h_pairs, uint32_t* h_paths);
 uint32_t b200zk_tree_depth(const b200zk_tree*);       /* log2 of the tallest height */
 uint32_t b200zk_tree_num_mats(const b200zk_tree*);
 uint64_t b200zk_tree_total_width(const b200zk_tree*); /* sum of widths = elements in h_rows */

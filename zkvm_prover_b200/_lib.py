@@ -98,6 +98,7 @@ _SIGS = {
     "b200zk_dev_free": (None, [_p, _p]),
     "b200zk_dev_upload": (_int, [_p, _p, _p, _u64]),
     "b200zk_dev_zero": (_int, [_p, _p, _u64]),
+    "b200zk_fri_open_queries": (_int, [_p, _p, _u32, _p, _u32, _p, _p]),
     "b200zk_ext_powers": (_int, [_p, _p, _u32, _p]),
     "b200zk_open_reduce": (_int, [_p, _p, _u32, _u32, _p, _p, _p, _p, _u32, _p, _p]),
     "b200zk_dev_download": (_int, [_p, _p, _p, _u64]),

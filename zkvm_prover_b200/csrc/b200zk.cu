@@ -1213,6 +1213,53 @@ int b200zk_merkle_open_many(b200zk_ctx* ctx, const b200zk_tree* t, const uint64_
     return B200ZK_OK;
 }
 
+// the FRI query phase over ALL commit-phase trees at once: tree r is opened at (index >> r) >> 1 for every query index.
+// One launch per tree, one upload of the indices and one download of everything (the per-tree call pays a
+// synchronisation per round: 20 rounds x 100 queries cost 4 ms of a 45 ms segment that way).
+//   h_pairs: n_trees x n_idx x 8 (the opened (lo, hi) EF4 pair), h_paths: tree after tree, n_idx x depth_r x 8
+int b200zk_fri_open_queries(b200zk_ctx* ctx, const b200zk_tree* const* trees, uint32_t n_trees, const uint64_t* h_indices, uint32_t n_idx, uint32_t* h_pairs,
+                            uint32_t* h_paths) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!n_trees || !n_idx) return B200ZK_OK;
+    if (!trees || !h_indices || !h_pairs || !h_paths) return fail(ctx, B200ZK_ERR_ARG, "null argument");
+    if (n_idx > 65535) return fail(ctx, B200ZK_ERR_ARG, "at most 65535 indices per call");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> idx((size_t)n_trees * n_idx);
+    size_t path_words = 0;
+    for (uint32_t r = 0; r < n_trees; r++) {
+        const b200zk_tree* t = trees[r];
+        if (!t || t->mats.size() != 1 || t->total_width != 8) return fail(ctx, B200ZK_ERR_ARG, "not a FRI commit-phase tree");
+        for (uint32_t q = 0; q < n_idx; q++) {
+            const uint64_t i = r < 63 ? (h_indices[q] >> r) >> 1 : 0;
+            if (i >= t->max_h) return fail(ctx, B200ZK_ERR_ARG, "index out of range");
+            idx[(size_t)r * n_idx + q] = i;
+        }
+        path_words += 8ull * t->depth * n_idx;
+        TRY(ensure_open(ctx, const_cast<b200zk_tree*>(t)));
+    }
+    const size_t pair_words = 8ull * n_trees * n_idx;
+    uint32_t* d = nullptr;
+    TRY(dev_alloc(ctx, (pair_words + path_words) * 4 + 8ull * idx.size() + 16, (void**)&d));
+    uint64_t* d_idx = reinterpret_cast<uint64_t*>(d + ((pair_words + path_words + 1) & ~(size_t)1));
+    cudaError_t e = cudaMemcpyAsync(d_idx, idx.data(), 8ull * idx.size(), cudaMemcpyHostToDevice, ctx->stream);  // pageable: staged before returning
+    size_t poff = 0;
+    for (uint32_t r = 0; r < n_trees && e == cudaSuccess; r++) {
+        const b200zk_tree* t = trees[r];
+        dim3 grid(1, n_idx);
+        mk::open_many_kernel<<<grid, 128, 0, ctx->stream>>>(t->d_open, 1, d_idx + (size_t)r * n_idx, n_idx, 8, t->d_digests, t->max_h, t->depth,
+                                                             d + 8ull * r * n_idx, d + pair_words + poff);
+        ctx->launches++;
+        poff += 8ull * t->depth * n_idx;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_pairs, d, pair_words * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && path_words) e = cudaMemcpyAsync(h_paths, d + pair_words, path_words * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, d);
+    if (e != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
+    return B200ZK_OK;
+}
+
 int b200zk_merkle_verify(b200zk_ctx* ctx, const uint32_t* h_rows, const uint64_t* heights, const uint32_t* widths, uint32_t k, const uint32_t* h_path,
                          uint32_t depth, uint64_t index, const uint32_t h_root[8], int* h_ok) {
     if (!ctx) return B200ZK_ERR_ARG;

@@ -253,10 +253,20 @@ class TwoAdicFriPcs:
         for pd, _ in rounds:
             lmh = max(m.rows for m in pd.mats).bit_length() - 1
             input_openings.append(self.mmcs.open_batch_many([i >> (log_max - lmh) for i in indices], pd))
+        # commit-phase openings of every round in one call (one download instead of a synchronisation per round)
         cp_openings = []
-        for r, tree in enumerate(res.data):
-            opens = self.mmcs.open_batch_many([(i >> r) >> 1 for i in indices], tree)
-            cp_openings.append([(vals[0].reshape(2, 4), path) for vals, path in opens])
+        if res.data:
+            nq, depths = len(indices), [t.depth for t in res.data]
+            idx = np.ascontiguousarray(indices, dtype=np.uint64)
+            pairs = np.empty((len(res.data), nq, 8), np.uint32)
+            paths = np.empty(8 * nq * sum(depths), np.uint32)
+            arr = (C.c_void_p * len(res.data))(*[t.h for t in res.data])
+            self.ctx.check(self.ctx.lib.b200zk_fri_open_queries(self.ctx.h, arr, len(res.data), idx.ctypes.data, nq, pairs.ctypes.data, paths.ctypes.data))
+            off = 0
+            for r, d in enumerate(depths):
+                pr = paths[off:off + 8 * nq * d].reshape(nq, d, 8)
+                off += 8 * nq * d
+                cp_openings.append([(pairs[r, q].reshape(2, 4), pr[q]) for q in range(nq)])
         proof = {"alpha": alpha, "commit_phase_commits": res.commits, "betas": res.betas, "final_poly": res.final_poly_coeffs,
                  "pow_witness": pow_witness, "query_indices": indices, "input_openings": input_openings, "commit_phase_openings": cp_openings,
                  "log_max_height": log_max}
