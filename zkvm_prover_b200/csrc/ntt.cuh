@@ -379,7 +379,7 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
                 mbar_expect_tx(full + b, tile_bytes);
                 tma_load_4d(bufs + b * (tile_bytes / 4), &in_map, full + b, c0, c1, 0, c3);
             };
-            for (uint32_t i = 0; i < my_tiles && i < (uint32_t)(TMA_STAGES - 1); i++) load(i);
+            for (uint32_t i = 0; i < my_tiles && i < (uint32_t)TMA_STAGES; i++) load(i);
             for (uint32_t c = 0; c < my_tiles; c++) {
                 const int b = c % TMA_STAGES;
                 mbar_wait(done + b, (c / TMA_STAGES) & 1);       // consumers are finished with tile c (they fenced the async proxy)
@@ -391,12 +391,12 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
                 }
                 tma_store_4d(&out_map, bufs + b * (tile_bytes / 4), c0, c1, 0, c3);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (c + (TMA_STAGES - 1) < my_tiles) {
-                    // the buffer of tile c+STAGES-1 last held tile c-1 (3 stages) or tile c itself (2 stages): that store
-                    // must have finished reading shared memory
-                    if (TMA_STAGES >= 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    load(c + (TMA_STAGES - 1));
+                if (c + TMA_STAGES < my_tiles) {
+                    // Refill THIS buffer as soon as its store has drained it from shared memory (about a microsecond), not when
+                    // the consumers finish the next tile: every stage of the ring then holds a tile in flight, i.e. the loads run
+                    // STAGES - 1 tiles ahead of the consumers instead of one (ncu r01: waiting for a tile was their top stall).
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    load(c + TMA_STAGES);
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -428,8 +428,10 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
                 fac_post[t] = shoup_pair(pow2level(p.tw_lo, p.tw_hi, e));
             }
         }
-        mbar_wait(full + b, (c / TMA_STAGES) & 1);
-        asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");  // factors visible to every consumer
+        // one warp polls the mbarrier, the other seven sleep in the hardware barrier below: eight polling warps spent 14 % of
+        // the kernel's issue slots on try_wait / branch (ncu r01), slots the other CTA of the SM needs for butterflies
+        if (tid < 32) mbar_wait(full + b, (c / TMA_STAGES) & 1);
+        asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");  // tile landed (observed by warp 0) and factors visible to every consumer
         int u = 0;
         const uint2* pre = fac_pre;
         auto post_if_last = [&](int stages) { return (u + stages == K) ? (const uint2*)fac_post : (const uint2*)nullptr; };
