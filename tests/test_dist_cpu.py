@@ -51,7 +51,7 @@ def _worker(rank, world, port, n, w, added_bits, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,w", [(2, 64, 16), (4, 32, 8)])
+@pytest.mark.parametrize("world,n,w", [(2, 64, 16), (4, 32, 8), (2, 32, 64)])   # the last one runs 4 column strips per rank
 def test_sharded_lde_commit_matches_single_device(tmp_path, world, n, w):
     added_bits = 1
     mp.spawn(_worker, args=(world, _free_port(), n, w, added_bits, str(tmp_path)), nprocs=world, join=True)

@@ -43,7 +43,7 @@ def test_sharded_commit_on_gpus(tmp_path):
     world = 2
     if torch.cuda.device_count() < world:
         pytest.skip("needs >= 2 GPUs")
-    mp.spawn(_worker, args=(world, _free_port(), 1 << 14, 64, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 1 << 14, 128, str(tmp_path)), nprocs=world, join=True)   # 64 columns per rank: 4 pipelined strips
     single = np.load(tmp_path / "single.npy")
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"root{r}.npy"), single)

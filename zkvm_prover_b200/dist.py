@@ -88,24 +88,52 @@ def combine_cap(cap: np.ndarray, compress) -> np.ndarray:
     return layer[0]
 
 
-def sharded_lde_commit(ops, local_cols, added_bits: int, shift: int, group=None):
+def _all_to_all_start(recv: torch.Tensor, send: torch.Tensor, group=None):
+    """begin recv[s] <- block `rank` of rank s's `send`; returns a waitable (None when it already completed)"""
+    try:
+        if dist.get_backend(group) != "gloo":
+            return dist.all_to_all_single(recv.view(-1), send.view(-1), group=group, async_op=True)
+    except Exception:
+        pass
+    _all_to_all_equal(recv, send, group)
+    return None
+
+
+def sharded_lde_commit(ops, local_cols, added_bits: int, shift: int, group=None, strips: int = 4):
     """Every rank holds a column shard (N x W/G, same N and W/G everywhere) of one trace matrix.
-    Returns (root[8] -- identical on all ranks and to the single-GPU commit of the full LDE --, cap (G,8))."""
+    Returns (root[8] -- identical on all ranks and to the single-GPU commit of the full LDE --, cap (G,8)).
+
+    The shard is extended in `strips` column strips; the all-to-all of strip j (NCCL, its own stream) runs while strip j+1 is
+    being extended, so only the last strip's exchange is exposed before the hashing starts.  The sponge absorbs the
+    columns in global order: rank 0's strips first, then rank 1's, ..."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if world & (world - 1):
         raise ValueError("the number of ranks must be a power of two")
     local = local_cols if isinstance(local_cols, torch.Tensor) else ops.to_device(local_cols)
-    lde = ops.lde(local, added_bits, shift)                 # (M, Wg), rows in bit-reversed order
-    m, wg = lde.shape
-    if m % world:
-        raise ValueError("LDE height must be divisible by the number of ranks")
-    mg = m // world
-    send = lde.view(world, mg, wg)                          # row block r goes to rank r
-    recv = torch.empty_like(send)
-    _all_to_all_equal(recv, send, group)                    # recv[s] = my row block of rank s's columns
-    root_local = ops.subtree_root([recv[s] for s in range(world)])  # sponge over the G column shards in order
-    cap_t = [torch.zeros(8, dtype=torch.int64, device=lde.device) for _ in range(world)]
-    dist.all_gather(cap_t, torch.from_numpy(root_local.astype(np.int64)).to(lde.device), group=group)
+    wg = local.shape[1]
+    if strips < 1 or wg % strips or (wg // strips) % 8:
+        strips = 1                                          # keep every exchanged block a whole number of sponge chunks
+    ws = wg // strips
+    recvs, pending = [], []
+    for j in range(strips):
+        part = local if strips == 1 else local[:, j * ws:(j + 1) * ws].contiguous()
+        lde = ops.lde(part, added_bits, shift)              # (M, ws), rows in bit-reversed order; returns when it is complete
+        m = lde.shape[0]
+        if m % world:
+            raise ValueError("LDE height must be divisible by the number of ranks")
+        mg = m // world
+        send = lde.view(world, mg, ws)                      # row block r goes to rank r
+        recv = torch.empty_like(send)
+        pending.append((_all_to_all_start(recv, send, group), send))   # keep `send` alive until the exchange is done
+        recvs.append(recv)                                  # recv[s] = my row block of rank s's strip j
+    for work, _ in pending:
+        if work is not None:
+            work.wait()
+    chunks = [recvs[j][s] for s in range(world) for j in range(strips)]   # global column order
+    root_local = ops.subtree_root(chunks)                   # one sponge over all chunks, then the subtree of my rows
+    dev = recvs[0].device
+    cap_t = [torch.zeros(8, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(cap_t, torch.from_numpy(root_local.astype(np.int64)).to(dev), group=group)
     cap = np.stack([c.cpu().numpy().astype(np.uint32) for c in cap_t])
     return combine_cap(cap, ops.compress), cap
