@@ -197,6 +197,19 @@ int b200zk_open_reduce(b200zk_ctx*, const b200zk_mat* lde, uint32_t log_blowup, 
 int b200zk_reduce_openings(b200zk_ctx*, const uint32_t* d_reduced_row, uint64_t m, const uint32_t* d_inv_den, const uint32_t h_reduced_ys[4],
                            const uint32_t h_alpha_pow_offset[4], uint32_t* d_ro);
 
+/* ---- multi-GPU: one wide matrix sharded by columns.  One process per GPU; a receive buffer is a cudaMalloc
+ *      allocation exported to the other ranks through a 64-byte CUDA IPC handle ------------------------------------------- */
+int b200zk_peer_alloc(b200zk_ctx*, uint64_t bytes, void** d_out, uint8_t h_handle[64]);
+int b200zk_peer_open(b200zk_ctx*, const uint8_t h_handle[64], void** d_out);   /* map another rank's buffer into this process */
+int b200zk_peer_close(b200zk_ctx*, void* d_peer);
+int b200zk_peer_free(b200zk_ctx*, void* d);
+/* Coset LDE of this rank's column shard (N x wg) whose result leaves in row blocks: the last NTT pass stores every finished tile with
+ * TMA straight into the memory of the rank that owns those rows -- d_recv[r] (own buffer or a peer mapping), laid out
+ * [world senders][M / world rows][wg] -- so the exchange needs no all-to-all and no staging copy.  Bit-reversed row order.
+ * Synchronise the stream and the ranks before reading the receive buffer. */
+int b200zk_coset_lde_scatter(b200zk_ctx*, const b200zk_mat* evals, uint32_t added_bits, uint32_t shift_monty, uint32_t world, uint32_t rank,
+                             uint32_t* const* d_recv);
+
 /* ---- raw device memory helpers for FFI users that do not bring their own allocator ------------------ */
 int b200zk_dev_alloc(b200zk_ctx*, uint64_t bytes, void** d_out);
 void b200zk_dev_free(b200zk_ctx*, void* d_ptr);

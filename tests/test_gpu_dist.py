@@ -29,6 +29,13 @@ def _worker(rank, world, port, n, w, out_dir):
         local = np.ascontiguousarray(full[:, rank * wg:(rank + 1) * wg])
         root, cap = D.sharded_lde_commit(D.GpuOps(ctx), local, 1, z.GENERATOR_MONTY)
         np.save(os.path.join(out_dir, f"root{rank}.npy"), root)
+        # the same with the exchange fused into the last NTT pass (TMA stores into the peer's receive buffer), twice on one mapping
+        exch = D.PeerExchange(ctx, 2 * n, wg)
+        for rep in range(2):
+            root2, cap2 = D.sharded_lde_commit_p2p(ctx, ctx.upload(local), 1, z.GENERATOR_MONTY, exch)
+            assert np.array_equal(cap2, cap), (rank, rep)
+            np.save(os.path.join(out_dir, f"p2p{rank}.npy"), root2)
+        exch.close()
         if rank == 0:  # single-GPU reference on the same device
             pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=1), ctx)
             r1, _ = pcs.commit([full])
@@ -47,3 +54,4 @@ def test_sharded_commit_on_gpus(tmp_path):
     single = np.load(tmp_path / "single.npy")
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"root{r}.npy"), single)
+        assert np.array_equal(np.load(tmp_path / f"p2p{r}.npy"), single)

@@ -259,8 +259,16 @@ struct Scale {
 
 // n-stage DIF over `rows = 2^n` rows.  src -> dst (first pass), then in place on dst; when out_natural the
 // last pass scatters into dst_final (which must not alias its source).
+// Destination of a sharded LDE (b200zk_coset_lde_scatter): the finished rows do not stay on this GPU, the last pass stores its
+// tiles straight into the row-block owner's memory (a peer mapping) with TMA.  Rows g0 .. g0 + 2^n of the whole LDE are
+// produced by this transform; rank r owns rows [r * mg, (r + 1) * mg) and keeps them at dst[r] + slot_off, pitch = width.
+struct Scatter {
+    uint32_t* const* dst = nullptr;
+    uint64_t g0 = 0, mg = 0, slot_off = 0;
+};
+
 int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t* dst_final, int n, uint32_t width, int inverse, Scale pre,
-                  Scale post, int out_natural, uint32_t src_pitch = 0, uint32_t work_pitch = 0, uint32_t dst_pitch = 0) {
+                  Scale post, int out_natural, uint32_t src_pitch = 0, uint32_t work_pitch = 0, uint32_t dst_pitch = 0, const Scatter* scatter = nullptr) {
     if (!src_pitch) src_pitch = width;
     if (!work_pitch) work_pitch = width;
     if (!dst_pitch) dst_pitch = width;
@@ -301,6 +309,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         p.post_lo = last ? post.lo : nullptr;
         p.post_hi = last ? post.hi : nullptr;
         p.out_natural = last ? out_natural : 0;
+        p.rt_base = 0;
         {
             const char* e = getenv("B200ZK_NTT_PREFETCH");  // experiment knob: CTAs of look-ahead (0 disables)
             p.prefetch_dist = e ? (uint32_t)atoi(e) : 148u; // measured best look-ahead (profiles/ntt_tuning_r01.txt)
@@ -316,6 +325,28 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             if (tiles > 0xffffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
             ntt::TensorMap in_map, out_map;
             TRY(make_pass_map(ctx, p.in, width, p.in_pitch, n, s0, K, tl, &in_map));
+            if (last && scatter) {
+                // one launch per destination: the row tiles [rt0, rt1) of this pass are the rows of one owner (L = 0 here)
+                const uint64_t R2 = 1ull << K, rows = 1ull << n;
+                if (scatter->mg % R2) return fail(ctx, B200ZK_ERR_SHAPE, "row block smaller than a tile");
+                const size_t tsm2 = 128 + (size_t)ntt::TMA_STAGES * (R2 * tcols * 4) + (2 * std::max<uint64_t>(R2 / 2, 1) + 4 * R2) * 4;
+                for (uint64_t g = scatter->g0; g < scatter->g0 + rows;) {
+                    const uint64_t r = g / scatter->mg;
+                    const uint64_t g_end = std::min(scatter->g0 + rows, (r + 1) * scatter->mg);
+                    const uint64_t n_rt = (g_end - g) >> K;                                  // a power of two
+                    uint32_t* base = scatter->dst[r] + scatter->slot_off + (g - r * scatter->mg) * width;
+                    const int nv = log2u(n_rt << K);
+                    TRY(make_pass_map(ctx, base, width, width, nv, nv - K, K, tl, &out_map));
+                    p.rt_base = (uint32_t)((g - scatter->g0) >> K);
+                    const uint64_t ntile = n_rt * ((width + tcols - 1) / tcols);
+                    const uint32_t grid2 = (uint32_t)std::min<uint64_t>(ntile, (uint64_t)NTT_TMA_CTAS * ctx->num_sms);
+                    ntt::pass_kernel_tma<<<grid2, ntt::TMA_THREADS, tsm2, ctx->stream>>>(in_map, out_map, p, (uint32_t)ntile);
+                    LAUNCHED();
+                    g = g_end;
+                }
+                s0 += K;
+                continue;
+            }
             if (p.out_natural) TRY(make_natural_map(ctx, p.out, width, p.out_pitch, n, K, tl, &out_map));
             else TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
             // (dynamic shared memory limits are raised once per device in configure_kernels)
@@ -326,6 +357,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             s0 += K;
             continue;
         }
+        if (last && scatter) return fail(ctx, B200ZK_ERR_SHAPE, "sharded LDE needs the TMA pass (width % 4 == 0, 16-byte aligned buffers)");
         const size_t smem = (R * tile_cols + 2 * std::max<uint64_t>(R / 2, 1) + R) * 4;
         const uint64_t blocks = ((1ull << n) >> K) * col_tiles;
         if (blocks > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
@@ -602,7 +634,8 @@ int lde_tables(b200zk_ctx* ctx, int n, uint32_t added_bits, uint32_t shift) {
 // (pitches in elements).  Needs lde_tables() for the same (n, added_bits, shift) to have been enqueued.
 // Work space is the destination itself: block 0 holds the inverse transform in flight, the natural-order coefficients
 // land in the last block, and every coset block is produced from them (the last one in place).
-int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, uint32_t width, uint32_t added_bits, uint32_t* dst, uint32_t dst_pitch) {
+int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, uint32_t width, uint32_t added_bits, uint32_t* dst, uint32_t dst_pitch,
+             const Scatter* scatter = nullptr) {
     const uint64_t N = 1ull << n;
     const uint32_t C = 1u << added_bits;
     const size_t per = lo_words(N) + hi_words(N);
@@ -619,7 +652,12 @@ int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, ui
     for (uint32_t c = 0; c < C && rc == B200ZK_OK; c++) {  // the block holding the coefficients goes last (in place)
         uint32_t* blk = dst + (uint64_t)c * N * dst_pitch;
         Scale pre{ctx->tab + per * c, ctx->tab + per * c + lo_words(N)};
-        rc = run_transform(ctx, coef, blk, blk, n, width, /*inverse=*/0, pre, Scale{}, 0, dst_pitch, dst_pitch, dst_pitch);
+        Scatter sc;
+        if (scatter) {
+            sc = *scatter;
+            sc.g0 = (uint64_t)c * N;  // this coset block is rows [c N, (c + 1) N) of the LDE
+        }
+        rc = run_transform(ctx, coef, blk, blk, n, width, /*inverse=*/0, pre, Scale{}, 0, dst_pitch, dst_pitch, dst_pitch, scatter ? &sc : nullptr);
     }
     if (tmp_inv) b200zk_mat_free(ctx, tmp_inv);
     return rc;
@@ -1664,6 +1702,86 @@ int b200zk_reduce_openings(b200zk_ctx* ctx, const uint32_t* d_rr, uint64_t m, co
     LAUNCHED();
     dev_free(ctx, d_c);
     return B200ZK_OK;
+}
+
+// ================================================================================================ peer memory (multi-GPU)
+// One process per GPU: a buffer other ranks store into is a plain cudaMalloc allocation exported with a CUDA IPC handle.
+int b200zk_peer_alloc(b200zk_ctx* ctx, uint64_t bytes, void** d_out, uint8_t h_handle[64]) {
+    if (!ctx || !d_out || !h_handle) return B200ZK_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(ctx->device));
+    *d_out = nullptr;
+    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cache_flush(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        e = cudaMalloc(d_out, bytes ? bytes : 16);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, B200ZK_ERR_OOM, std::string("cudaMalloc (peer buffer): ") + cudaGetErrorString(e));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, *d_out));
+    memcpy(h_handle, &h, 64);
+    return B200ZK_OK;
+}
+int b200zk_peer_open(b200zk_ctx* ctx, const uint8_t h_handle[64], void** d_out) {
+    if (!ctx || !d_out || !h_handle) return B200ZK_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle, 64);
+    CU(cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200ZK_OK;
+}
+int b200zk_peer_close(b200zk_ctx* ctx, void* d_peer) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d_peer) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaIpcCloseMemHandle(d_peer));
+    return B200ZK_OK;
+}
+int b200zk_peer_free(b200zk_ctx* ctx, void* d) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!d) return B200ZK_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(d));
+    return B200ZK_OK;
+}
+
+// Column-sharded coset LDE whose result leaves in ROW blocks: this rank extends its `evals` (N x wg columns of the trace) and the last
+// NTT pass of every coset stores each finished tile with TMA directly into the memory of the rank that owns those rows
+// (d_recv[r], local or a peer mapping), at slot `rank` of that rank's [world][M / world][wg] receive buffer.  The exchange
+// rides on the stores of the pass: no separate all-to-all, no staging copy.  Callers synchronise (stream sync + a
+// barrier across the ranks) before reading their receive buffer.
+int b200zk_coset_lde_scatter(b200zk_ctx* ctx, const b200zk_mat* evals, uint32_t added_bits, uint32_t shift, uint32_t world, uint32_t rank,
+                             uint32_t* const* d_recv) {
+    TRY(check_mat(ctx, evals));
+    if (!d_recv || !world || rank >= world || (world & (world - 1))) return fail(ctx, B200ZK_ERR_ARG, "bad world / rank / receive buffers");
+    const uint64_t N = evals->rows;
+    const uint32_t W = evals->width;
+    if (!is_pow2(N) || N < 2) return fail(ctx, B200ZK_ERR_SHAPE, "height must be a power of two >= 2");
+    const int n = log2u(N);
+    if (n + (int)added_bits > MAX_LOG) return fail(ctx, B200ZK_ERR_SHAPE, "size exceeds the two-adicity of BabyBear (2^27)");
+    if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
+    const uint64_t M = N << added_bits;
+    if (M % world) return fail(ctx, B200ZK_ERR_SHAPE, "LDE height must be divisible by the number of ranks");
+    if (W % 4) return fail(ctx, B200ZK_ERR_SHAPE, "sharded LDE needs width % 4 == 0");
+    for (uint32_t r = 0; r < world; r++)
+        if (!d_recv[r] || ((uintptr_t)d_recv[r] % 16)) return fail(ctx, B200ZK_ERR_ARG, "null / misaligned receive buffer");
+    CU(cudaSetDevice(ctx->device));
+    b200zk_mat* work = nullptr;  // local work space: every pass but the last of each coset runs here, exactly as in the unsharded LDE
+    TRY(b200zk_mat_alloc(ctx, M, W, &work));
+    int rc = lde_tables(ctx, n, added_bits, shift);
+    Scatter sc;
+    sc.dst = d_recv;
+    sc.mg = M / world;
+    sc.slot_off = (uint64_t)rank * sc.mg * W;
+    if (rc == B200ZK_OK) rc = lde_core(ctx, evals->d, W, n, W, added_bits, work->d, W, &sc);
+    b200zk_mat_free(ctx, work);
+    return rc;
 }
 
 // ================================================================================================ raw memory

@@ -47,6 +47,7 @@ struct PassParams {
     const uint32_t* post_lo;   // optional (last pass only): multiply logical output index j likewise
     const uint32_t* post_hi;
     int out_natural;      // last pass only: write logical index j = bitrev_n(position) to row j
+    uint32_t rt_base;     // TMA kernel: first row tile of this launch (a pass may be issued in several launches, one per destination)
     uint32_t prefetch_dist;  // CTAs resident at once: each CTA prefetches (to L2) the tile of block blockIdx.x + prefetch_dist
 };
 
@@ -367,7 +368,7 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
             auto coords = [&](uint32_t i, int& c0, int& c1, int& c3) {
                 const uint32_t tile = first + i * stride;
                 const uint32_t ct = tile % col_tiles;
-                const uint64_t rt = tile / col_tiles;
+                const uint64_t rt = tile / col_tiles + p.rt_base;
                 c0 = (int)(ct << lc);
                 c1 = (int)(rt & ((1ull << L) - 1));
                 c3 = (int)(rt >> L);
@@ -388,6 +389,8 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
                 if (p.out_natural) {  // last pass (L = 0): the tile leaves as rows k1 * 2^(n-K) + bitrev(high), k1 = 0..2^K-1
                     c1 = (int)bb::bitrev((uint32_t)c3, n - K);
                     c3 = 0;
+                } else {
+                    c3 -= (int)(p.rt_base >> L);  // the destination map of a partial launch starts at its own first row tile
                 }
                 tma_store_4d(&out_map, bufs + b * (tile_bytes / 4), c0, c1, 0, c3);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -411,7 +414,7 @@ pass_kernel_tma(const __grid_constant__ TensorMap in_map, const __grid_constant_
         const int b = c % TMA_STAGES;
         uint32_t* sm = bufs + b * (tile_bytes / 4);
         const uint32_t tile = first + c * stride;
-        const uint64_t rt = tile / col_tiles;
+        const uint64_t rt = tile / col_tiles + p.rt_base;
         const uint64_t low = rt & ((1ull << L) - 1);
         const uint64_t high = rt >> L;
         const uint64_t row_base = (high << (n - s0)) + low;

@@ -137,3 +137,76 @@ def sharded_lde_commit(ops, local_cols, added_bits: int, shift: int, group=None,
     dist.all_gather(cap_t, torch.from_numpy(root_local.astype(np.int64)).to(dev), group=group)
     cap = np.stack([c.cpu().numpy().astype(np.uint32) for c in cap_t])
     return combine_cap(cap, ops.compress), cap
+
+
+class PeerExchange:
+    """Receive buffers for `sharded_lde_commit_p2p`: every rank owns one [world][M / world][wg] buffer (cudaMalloc, exported through a
+    CUDA IPC handle) and maps the buffers of all other ranks, so the last NTT pass can store finished tiles straight into the
+    row-block owner's memory over NVLink.  Build once per shape, reuse for every commit."""
+
+    def __init__(self, ctx, rows_lde: int, wg: int, group=None):
+        self.ctx, self.group = ctx, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if rows_lde % self.world:
+            raise ValueError("LDE height must be divisible by the number of ranks")
+        self.mg, self.wg = rows_lde // self.world, wg
+        self.nbytes = 4 * rows_lde * wg
+        own, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        ctx.check(ctx.lib.b200zk_peer_alloc(ctx.h, self.nbytes, C.byref(own), handle))
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.own)
+                continue
+            p = C.c_void_p()
+            hb = (C.c_uint8 * 64).from_buffer_copy(h)
+            ctx.check(ctx.lib.b200zk_peer_open(ctx.h, hb, C.byref(p)))
+            self.ptrs.append(p.value)
+        self.ptr_array = (C.c_void_p * self.world)(*self.ptrs)
+
+    def chunk(self, sender: int):
+        """my row block of `sender`'s columns: an (mg, wg) matrix inside my receive buffer"""
+        return self.ctx.wrap(self.own + 4 * sender * self.mg * self.wg, self.mg, self.wg)
+
+    def close(self):
+        if getattr(self, "ptrs", None):
+            dist.barrier(self.group)   # nobody may still be storing into a buffer that is about to go away
+            for r, p in enumerate(self.ptrs):
+                if r != self.rank:
+                    self.ctx.lib.b200zk_peer_close(self.ctx.h, C.c_void_p(p))
+            dist.barrier(self.group)
+            self.ctx.lib.b200zk_peer_free(self.ctx.h, C.c_void_p(self.own))
+            self.ptrs = None
+
+
+def sharded_lde_commit_p2p(ctx, local_cols, added_bits: int, shift: int, exch: PeerExchange | None = None, group=None):
+    """`sharded_lde_commit` with the exchange fused into the transform: b200zk_coset_lde_scatter stores the finished tiles of the last
+    NTT pass directly into the owner's receive buffer (TMA over a peer mapping), so there is no all-to-all and no staging copy.
+    local_cols: this rank's column shard as a DeviceMatrix (N x wg).  Returns (root, cap) like `sharded_lde_commit`."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n, wg = local_cols.rows, local_cols.width
+    own_exch = exch is None
+    if own_exch:
+        exch = PeerExchange(ctx, n << added_bits, wg, group)
+    try:
+        dist.barrier(group)            # every rank is done reading its receive buffer from the previous call
+        ctx.check(ctx.lib.b200zk_coset_lde_scatter(ctx.h, local_cols.h, added_bits, shift, world, rank, exch.ptr_array))
+        ctx.sync()                     # my stores (local and remote) are complete ...
+        dist.barrier(group)            # ... and so are everybody else's into my buffer
+        chunks = [exch.chunk(s) for s in range(world)]
+        arr = (C.c_void_p * world)(*[m.h for m in chunks])
+        root_local = np.empty(8, np.uint32)
+        t = C.c_void_p()
+        ctx.check(ctx.lib.b200zk_merkle_commit(ctx.h, arr, world, 0, root_local.ctypes.data, C.byref(t)))
+        ctx.lib.b200zk_tree_free(ctx.h, t)
+        dev = torch.device("cuda", ctx.device)
+        cap_t = [torch.zeros(8, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(cap_t, torch.from_numpy(root_local.astype(np.int64)).to(dev), group=group)
+        cap = np.stack([c.cpu().numpy().astype(np.uint32) for c in cap_t])
+        return combine_cap(cap, GpuOps(ctx).compress), cap
+    finally:
+        if own_exch:
+            exch.close()
