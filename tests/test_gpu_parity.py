@@ -152,6 +152,41 @@ def test_merkle_errors(z, ctx):
     assert e.value.code == -4
 
 
+def test_batched_and_sharded_entry_points_reject_bad_arguments(z, ctx):
+    """error behaviour of the entry points added for the query phase, the fused open step and the sharded LDE: misuse is an
+    error code (ERR_ARG = -4, ERR_SHAPE = -3), never a crash or a silent result"""
+    lib = ctx.lib
+    mmcs = z.MerkleTreeMmcs(ctx)
+    root, pd = mmcs.commit([rnd((8, 2), 1)])                      # an ordinary tree is not a FRI commit-phase tree (leaves must be 8 wide)
+    idx = np.array([1, 2], np.uint64)
+    pairs, paths = np.zeros((1, 2, 8), np.uint32), np.zeros(64, np.uint32)
+    arr = (C.c_void_p * 1)(pd.h)
+    assert lib.b200zk_fri_open_queries(ctx.h, arr, 1, idx.ctypes.data, 2, pairs.ctypes.data, paths.ctypes.data) == -4
+    assert lib.b200zk_fri_open_queries(ctx.h, arr, 1, None, 2, pairs.ctypes.data, paths.ctypes.data) == -4
+    assert lib.b200zk_fri_open_queries(ctx.h, arr, 0, idx.ctypes.data, 2, pairs.ctypes.data, paths.ctypes.data) == 0   # nothing to do
+    m = ctx.upload(rnd((16, 6), 2))                                # width 6: not a multiple of 4
+    buf = z.DeviceBuffer(ctx, 4 * 32 * 8)
+    ptrs = (C.c_void_p * 2)(buf.ptr, buf.ptr)
+    assert lib.b200zk_coset_lde_scatter(ctx.h, m.h, 1, z.GENERATOR_MONTY, 2, 0, ptrs) == -3
+    m4 = ctx.upload(rnd((16, 8), 3))
+    assert lib.b200zk_coset_lde_scatter(ctx.h, m4.h, 1, z.GENERATOR_MONTY, 3, 0, ptrs) == -4      # world must be a power of two
+    assert lib.b200zk_coset_lde_scatter(ctx.h, m4.h, 1, z.GENERATOR_MONTY, 2, 2, ptrs) == -4      # rank out of range
+    assert lib.b200zk_coset_lde_scatter(ctx.h, m4.h, 1, 0, 2, 0, ptrs) == -4                      # zero shift
+    assert lib.b200zk_coset_lde_scatter(ctx.h, m4.h, 1, z.GENERATOR_MONTY, 2, 0, None) == -4
+    zp = rnd(4, 5)
+    assert lib.b200zk_open_reduce(ctx.h, m4.h, 1, z.GENERATOR_MONTY, zp.ctypes.data, buf.ptr, None, buf.ptr, 0, buf.ptr, buf.ptr) == -4
+    assert lib.b200zk_ext_powers(ctx.h, None, 4, buf.ptr) == -4
+    assert lib.b200zk_ext_powers(ctx.h, zp.ctypes.data, 0, None) == 0
+    assert lib.b200zk_dev_zero(ctx.h, None, 16) == -4
+    # a single-rank "sharded" LDE is just the LDE: the scatter path with world = 1 must reproduce it
+    out = z.DeviceBuffer(ctx, 4 * 32 * 8)
+    one = (C.c_void_p * 1)(out.ptr)
+    src = rnd((16, 8), 6)
+    msrc = ctx.upload(src)                                         # keep the handle alive across the call
+    ctx.check(lib.b200zk_coset_lde_scatter(ctx.h, msrc.h, 1, z.GENERATOR_MONTY, 1, 0, one))
+    assert np.array_equal(out.to_host((32, 8)), O.coset_lde_batch(src, 1, z.GENERATOR_MONTY, bitrev_out=True))
+
+
 # ------------------------------------------------------------------------------------------ K2 NTT / LDE
 @pytest.mark.parametrize("n,w", [(0, 3), (1, 1), (2, 5), (3, 4), (5, 32), (9, 36), (10, 8), (11, 3), (13, 64), (14, 4), (18, 4), (19, 4), (21, 4)])
 def test_dft_batch_matches_oracle(z, ctx, n, w):
