@@ -9,7 +9,7 @@ import numpy as np
 
 from .challenger import DuplexChallenger
 from .device import Context, DeviceBuffer, DeviceMatrix, default_context
-from .field import GENERATOR_MONTY, P, ef_add, ef_dot, ef_mul, ef_pow, ef_powers, ef_scale_base, from_monty, monty_scalar, two_adic_generator
+from .field import GENERATOR_MONTY, P, from_monty, monty_scalar
 from .mmcs import DIGEST, MerkleTreeMmcs, ProverData
 
 
