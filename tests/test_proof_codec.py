@@ -116,3 +116,36 @@ def test_reference_fixtures_reencode_byte_identically():
             assert p.main_trace_commits[0].tolist() == kats["b3_single_matrix"]["root"]
         seen += 1
     assert seen == len(GOLD["fixtures"])
+
+
+def test_property_random_structures_round_trip():
+    """hypothesis: arbitrary shapes (empty vectors, zero-depth paths, zero queries, many AIRs) survive encode -> decode -> encode"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2**32 - 1), n_air=st.integers(0, 5), n_q=st.integers(0, 3), rounds=st.integers(0, 4), logup=st.booleans(),
+           n_pv=st.integers(0, 40))
+    def run(seed, n_air, n_q, rounds, logup, n_pv):
+        rng = np.random.default_rng(seed)
+
+        def adj(w):
+            return W.AdjacentOpenedValues(_rnd(rng, w, 4), _rnd(rng, w, 4))
+
+        queries = [W.QueryProof([W.BatchOpening([_rnd(rng, int(w)) for w in rng.integers(0, 6, int(rng.integers(0, 4)))], _rnd(rng, int(rng.integers(0, 5)), 8))
+                                 for _ in range(int(rng.integers(0, 3)))],
+                                [W.CommitPhaseProofStep(_rnd(rng, 4), _rnd(rng, rounds - i, 8)) for i in range(rounds)]) for _ in range(n_q)]
+        fri = W.FriProof(_rnd(rng, rounds, 8), queries, _rnd(rng, int(rng.integers(0, 3)), 4), int(rng.integers(0, P)))
+        opened = W.OpenedValues([adj(int(rng.integers(0, 3))) for _ in range(int(rng.integers(0, 3)))],
+                                [[adj(int(rng.integers(0, 4))) for _ in range(n_air)] for _ in range(int(rng.integers(0, 3)))],
+                                [[adj(1) for _ in range(n_air)]],
+                                [[_rnd(rng, 4, 4) for _ in range(int(rng.integers(0, 3)))] for _ in range(n_air)])
+        per_air = [W.AirProofData(int(rng.integers(0, 100)), 1 << int(rng.integers(0, 20)), [_rnd(rng, int(rng.integers(0, 3)), 4)], _rnd(rng, int(rng.integers(0, 5))))
+                   for _ in range(n_air)]
+        proof = W.Proof(_rnd(rng, int(rng.integers(0, 3)), 8), _rnd(rng, int(rng.integers(0, 2)), 8), _rnd(rng, 8), fri, opened, per_air,
+                        int(rng.integers(0, P)) if logup else None)
+        v = W.VmInternalStarkProof([proof] * int(rng.integers(0, 3)), _rnd(rng, n_pv))
+        blob, pv = v.encode_proofs(), v.encode_public_values()
+        back = W.VmInternalStarkProof.decode(blob, pv)
+        assert _eq(back, v) and back.encode_proofs() == blob and back.encode_public_values() == pv
+
+    run()
