@@ -553,17 +553,31 @@ class TwoAdicFriPcs {
             auto opens = MerkleTreeMmcs(c).open_batch_many(idx, *r.data);
             for (size_t q = 0; q < indices.size(); q++) proof.query_proofs[q].input_proof.push_back(std::move(opens[q]));
         }
-        for (size_t rd = 0; rd < res.data.size(); rd++) {
-            std::vector<uint64_t> idx;
-            for (uint64_t q : indices) idx.push_back((q >> rd) >> 1);
-            auto opens = MerkleTreeMmcs(c).open_batch_many(idx, res.data[rd]);
-            for (size_t q = 0; q < indices.size(); q++) {
-                const std::vector<F>& pair = opens[q].opened_values.at(0);  // (lo, hi) of the queried pair, 8 words
-                const size_t sib = 1 - ((indices[q] >> rd) & 1);             // the proof carries the OTHER value
-                CommitPhaseProofStep st;
-                for (int k = 0; k < 4; k++) st.sibling_value[k] = pair[4 * sib + k];
-                st.opening_proof = std::move(opens[q].opening_proof);
-                proof.query_proofs[q].commit_phase_openings.push_back(std::move(st));
+        if (!res.data.empty()) {  // commit-phase openings of every round in one call (one download instead of one per round)
+            const size_t nq = indices.size(), nt = res.data.size();
+            std::vector<const b200zk_tree*> trees;
+            size_t path_words = 0;
+            for (auto& t : res.data) {
+                trees.push_back(t.raw());
+                path_words += 8ull * t.depth() * nq;
+            }
+            std::vector<F> pairs(8 * nt * nq), paths(path_words);
+            c.check(b200zk_fri_open_queries(c.raw(), trees.data(), (uint32_t)nt, indices.data(), (uint32_t)nq, pairs.data(), paths.data()));
+            size_t poff = 0;
+            for (size_t rd = 0; rd < nt; rd++) {
+                const size_t depth = res.data[rd].depth();
+                for (size_t q = 0; q < nq; q++) {
+                    const size_t sib = 1 - ((indices[q] >> rd) & 1);  // the proof carries the OTHER value of the queried pair
+                    CommitPhaseProofStep st;
+                    for (int k = 0; k < 4; k++) st.sibling_value[k] = pairs[(rd * nq + q) * 8 + 4 * sib + k];
+                    for (size_t l = 0; l < depth; l++) {
+                        Digest dg;
+                        for (int j = 0; j < 8; j++) dg[j] = paths[poff + (q * depth + l) * 8 + j];
+                        st.opening_proof.push_back(dg);
+                    }
+                    proof.query_proofs[q].commit_phase_openings.push_back(std::move(st));
+                }
+                poff += 8 * depth * nq;
             }
         }
         std::vector<F> ys(4 * total_cols);
