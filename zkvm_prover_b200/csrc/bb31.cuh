@@ -37,6 +37,8 @@ BB_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 #ifdef __CUDACC__
 static __device__ __constant__ uint32_t K_ONE = 1u;
 static __device__ __constant__ uint32_t K_ZERO = 0u;
+static __device__ __constant__ uint32_t K_MU = 0x88000001u;   // P^-1 mod 2^32, opaque to ptxas (see smulz)
+static __device__ __constant__ uint32_t K_27 = 27u, K_31 = 31u;
 #endif
 #ifdef __CUDA_ARCH__
 BB_HD uint32_t fadd(uint32_t a, uint32_t b) { return a * K_ONE + b; }
@@ -70,6 +72,40 @@ BB_HD int32_t smul(int32_t a, int32_t b) {
     int32_t qh = mulhi32(q, (int32_t)P);
     return (int32_t)asub((uint32_t)(t >> 32), (uint32_t)qh);
 }
+// The same product in three FMA-pipe instructions and no ALU instruction: IMAD.WIDE t = a*b; IMAD q = lo(t)*mu (+ z);
+// IMAD.WIDE r = q*(-p) + t, whose low word is zero by construction and whose high word is the result.  ptxas only keeps
+// the multiply-accumulate whole (64-bit addend next to an immediate multiplicand) if BOTH halves of r are used and if it
+// cannot prove the low half is zero: mu therefore comes from constant memory, and the low word is handed back in `z`
+// (always 0 at run time) for the caller to fold into a later instruction that has a free addend slot (here: the next
+// product's q).  Otherwise it falls back to IMAD.HI + IADD3/IADD3.X, which is slower than smul().
+#ifdef __CUDA_ARCH__
+BB_HD int32_t smulz(int32_t a, int32_t b, uint32_t& z) {
+    int64_t t;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
+    const uint32_t q = (uint32_t)t * K_MU + z;
+    const int64_t r = (int64_t)(int32_t)q * (int64_t)(-(int32_t)P) + t;
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(r));
+    z = lo;
+    return (int32_t)hi;
+}
+// q from shifts on the ALU pipe instead of an IMAD (mu = 2^31 + 2^27 + 1): 8 FMA-pipe clocks + 3-4 ALU instructions.
+// No addend slot is free here, so the incoming z is OR-ed into the outgoing one (ptxas merges two of these into one LOP3).
+BB_HD int32_t smulz_lea(int32_t a, int32_t b, uint32_t& z) {
+    int64_t t;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
+    const uint32_t l = (uint32_t)t;
+    const uint32_t q = l + (l << K_27) + (l << K_31);  // shift counts from constant memory: with immediates ptxas turns this back into IMADs
+    const int64_t r = (int64_t)(int32_t)q * (int64_t)(-(int32_t)P) + t;
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(r));
+    z |= lo;
+    return (int32_t)hi;
+}
+#else
+BB_HD int32_t smulz(int32_t a, int32_t b, uint32_t& z) { (void)z; return smul(a, b); }
+BB_HD int32_t smulz_lea(int32_t a, int32_t b, uint32_t& z) { (void)z; return smul(a, b); }
+#endif
 // canonical operands (any pair with |a*b| < 2^31 p, taken as signed) -> [0,p)
 BB_HD uint32_t mul(uint32_t a, uint32_t b) { return canon(smul((int32_t)a, (int32_t)b)); }
 // Montgomery reduction of 0 <= t < 2^31 * p -> [0,p)

@@ -67,7 +67,38 @@ BB_HD uint32_t sbox7(int32_t x) {
     return bb::canon(bb::smul(x3, x4));
 }
 
+// The same with bb::smulz (three FMA-pipe instructions per product, none on the ALU pipe).  The always-zero low words
+// are chained through the q of the next product of the chain (x2 -> x3 -> x4 -> x7; x4 is ordered behind x3 only for
+// that), so one S-box takes a z in and hands one z out.  P2_QLEA: this S-box derives its four q's with shifts on the ALU
+// pipe instead (bb::smulz_lea).
+template <bool QLEA>
+BB_HD uint32_t sbox7z(int32_t x, uint32_t& z) {
+    if (QLEA) {
+        int32_t x2 = bb::smulz_lea(x, x, z);
+        int32_t x3 = bb::smulz_lea(x2, x, z);
+        int32_t x4 = bb::smulz_lea(x2, x2, z);
+        return bb::canon(bb::smulz_lea(x3, x4, z));
+    }
+    int32_t x2 = bb::smulz(x, x, z);
+    int32_t x3 = bb::smulz(x2, x, z);
+    int32_t x4 = bb::smulz(x2, x2, z);
+    return bb::canon(bb::smulz(x3, x4, z));
+}
+
 // ---- tuning knobs (pipe assignment; see bb31.cuh "pipe model").  Defaults are the measured best.
+#ifndef P2_FUSED
+// S-box products: 1 = bb::smulz (IMAD.WIDE + IMAD + IMAD.WIDE with addend), 0 = bb::smul.  Measured on B200 (tools/p2_sweep_r02.sh,
+// profiles/poseidon2_sweep_r02.txt): the fused form has 64 fewer ALU instructions per external round and the same FMA-pipe
+// instruction count, and is 3-5 % SLOWER (4.13-4.24 vs 4.36 Gperm/s) -- the multiply-accumulate with a 64-bit addend does not issue
+// at the rate of the plain IMAD.WIDE.  Kept as an experiment knob.
+#define P2_FUSED 0
+#endif
+#ifndef P2_QLEA_MASK
+#define P2_QLEA_MASK 0x0000  // external rounds, fused form: lanes whose S-box computes q with shifts (ALU pipe) instead of an IMAD
+#endif
+#ifndef P2_QLEA_INT
+#define P2_QLEA_INT 0    // the same for the single S-box of an internal round
+#endif
 #ifndef P2_RC_FMA
 #define P2_RC_FMA 0      // round-constant additions on the FMA pipe (1) or ALU pipe (0)
 #endif
@@ -120,6 +151,20 @@ BB_HD void mds_light(uint32_t (&s)[16]) {
 BB_HD void external_round(uint32_t (&s)[16], const int32_t* rc) {
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = sbox7((int32_t)(P2_RC_FMA ? bb::fadd(s[i], (uint32_t)rc[i]) : bb::aadd(s[i], (uint32_t)rc[i])));
+    mds_light(s);
+}
+// fused-product form: z is the running always-zero word (see bb::smulz); every S-box starts from the round's incoming z
+// and the sixteen outgoing ones are OR-ed together (eight 3-input LOP3) into the next round's
+BB_HD void external_round_z(uint32_t (&s)[16], const int32_t* rc, uint32_t& z) {
+    uint32_t zo = z;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint32_t zi = z;
+        const int32_t x = (int32_t)(P2_RC_FMA ? bb::fadd(s[i], (uint32_t)rc[i]) : bb::aadd(s[i], (uint32_t)rc[i]));
+        s[i] = ((P2_QLEA_MASK >> i) & 1) ? sbox7z<true>(x, zi) : sbox7z<false>(x, zi);
+        zo |= zi;
+    }
+    z = zo;
     mds_light(s);
 }
 
@@ -176,8 +221,17 @@ BB_HD uint32_t sum16(const uint32_t (&s)[16]) {
 #endif
 
 #define P2_OUT_ADD(lvl, a, b) ((P2_INT_OUT_FMA >= (lvl)) ? add_f((a), (b)) : bb::add((a), (b)))
+BB_HD void internal_linear(uint32_t (&s)[16]);
 BB_HD void internal_round(uint32_t (&s)[16], int32_t rc) {
     s[0] = sbox7((int32_t)(P2_RC_FMA ? bb::fadd(s[0], (uint32_t)rc) : bb::aadd(s[0], (uint32_t)rc)));
+    internal_linear(s);
+}
+BB_HD void internal_round_z(uint32_t (&s)[16], int32_t rc, uint32_t& z) {
+    const int32_t x = (int32_t)(P2_RC_FMA ? bb::fadd(s[0], (uint32_t)rc) : bb::aadd(s[0], (uint32_t)rc));
+    s[0] = P2_QLEA_INT ? sbox7z<true>(x, z) : sbox7z<false>(x, z);
+    internal_linear(s);
+}
+BB_HD void internal_linear(uint32_t (&s)[16]) {
     const uint32_t sum = sum16(s);
     s[0] = lin_small<-2>(sum, s[0]);
     s[1] = P2_OUT_ADD(1, sum, s[1]);
@@ -202,6 +256,19 @@ BB_HD void internal_round(uint32_t (&s)[16], int32_t rc) {
 // rolled, the whole permutation is ~10 KB and the round constants come from constant memory.
 BB_HD void permute(uint32_t (&s)[16]) {
     mds_light(s);
+#if P2_FUSED && defined(__CUDA_ARCH__)
+    uint32_t z = bb::K_ZERO;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) external_round_z(s, P2_TAB.ext[4 * half + r], z);
+        if (half == 0) {
+#pragma unroll 1
+            for (int r = 0; r < 13; r++) internal_round_z(s, P2_TAB.in[r], z);
+        }
+    }
+    s[15] |= z;  // z == 0; this use is what keeps the low halves of the products alive (see bb::smulz)
+#else
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
 #pragma unroll 1
@@ -211,6 +278,7 @@ BB_HD void permute(uint32_t (&s)[16]) {
             for (int r = 0; r < 13; r++) internal_round(s, P2_TAB.in[r]);
         }
     }
+#endif
 }
 
 // straightforward variant (generic Montgomery multiplies everywhere); kept as an in-library cross-check
