@@ -153,7 +153,8 @@ int b200zk_chal_observe(b200zk_ctx*, b200zk_chal*, const uint32_t* h_values, uin
 int b200zk_chal_sample(b200zk_ctx*, b200zk_chal*, uint32_t* h_out, uint32_t n); /* n base elements, in order */
 int b200zk_chal_sample_bits(b200zk_ctx*, b200zk_chal*, uint32_t bits, uint32_t* h_out);
 /* GrindingChallenger::grind: smallest witness w (canonical) with sample_bits(bits)==0 after observe(w);
- * observes it.  (p3 uses a parallel find_any, so the CPU witness is any valid one, not necessarily this.) */
+ * observes it.  (p3 uses a parallel find_any, so the CPU witness is any valid one, not necessarily this.)
+ * bits == 0 follows p3-challenger 0.4.3 (the reference's pin, Cargo.lock:5576): witness 0, transcript untouched. */
 int b200zk_chal_grind(b200zk_ctx*, b200zk_chal*, uint32_t bits, uint32_t* h_witness);
 int b200zk_chal_state(b200zk_ctx*, const b200zk_chal*, uint32_t h_state[16 + 8 + 1 + 8 + 1]);
 

@@ -439,7 +439,7 @@ struct FriProof {
     std::vector<Digest> commit_phase_commits;
     std::vector<QueryProof> query_proofs;
     std::vector<EF4> final_poly;
-    F pow_witness = 0;
+    F pow_witness = 0;  // canonical witness (Challenger::grind); a field element on the wire, so encode() writes its Montgomery form
     std::vector<uint8_t> encode() const {
         std::vector<uint8_t> out;
         auto u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i))); };
@@ -459,7 +459,7 @@ struct FriProof {
         }
         u64(final_poly.size());
         for (auto& e : final_poly) for (F x : e) u32(x);
-        u32(pow_witness);
+        u32(field::to_monty(pow_witness));
         return out;
     }
 };

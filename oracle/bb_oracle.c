@@ -22,6 +22,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define P 0x78000001u
 #define MU 0x88000001u /* P^-1 mod 2^32 */
@@ -472,6 +475,7 @@ void orc_chal_sample_ext(orc_chal* c, u32* out4) { for (int i = 0; i < 4; i++) o
 u32 orc_chal_sample_bits(orc_chal* c, u32 bits) { return bb_from_monty(orc_chal_sample(c)) & ((1u << bits) - 1); }
 /* smallest PoW witness (canonical value returned); observes it like DuplexChallenger::grind */
 u32 orc_chal_grind(orc_chal* c, u32 bits) {
+    if (bits == 0) return 0; /* p3-challenger 0.4.3 GrindingChallenger: bits == 0 needs no witness and leaves the transcript alone */
     for (u32 w = 0; w < P; w++) {
         orc_chal t = *c;
         u32 wm = bb_to_monty(w);
@@ -526,4 +530,252 @@ u64 orc_checksum(const u32* v, u64 n, u64 offset) {
 #pragma omp parallel for reduction(+ : acc) schedule(static)
     for (u64 i = 0; i < n; i++) acc += splitmix64((offset + i) ^ ((u64)v[i] << 32));
     return acc;
+}
+
+
+/* ================================================================== AVX-512 fast path (bench.py CPU baseline only)
+ * The same algorithms with the data-parallel structure Plonky3's CPU code uses, so that the timed CPU baseline is not a scalar
+ * strawman: PackedBabyBearAVX512-style Montgomery arithmetic on 16 lanes (p3-monty-31 x86_64_avx512 packing), Poseidon2 over 16
+ * rows at a time (p3-merkle-tree hashes PackedValue::WIDTH rows per permutation), butterflies vectorised along the row
+ * (p3-dft Radix2DitParallel works on row-major matrices the same way) with two stages per sweep and cache-resident tails.
+ * Compiled only with -march=native on an AVX-512 host (`make native`); tests/test_oracle_kats.py checks it against the scalar
+ * restatement above, which stays the parity checker. */
+#if defined(__AVX512F__) && defined(__AVX512DQ__)
+#include <immintrin.h>
+#define ORC_AVX512 1
+typedef __m512i v16;
+#define VP _mm512_set1_epi32((int)P)
+#define VMU _mm512_set1_epi32((int)MU)
+static inline v16 v_add(v16 a, v16 b) { v16 s = _mm512_add_epi32(a, b); return _mm512_min_epu32(s, _mm512_sub_epi32(s, VP)); }
+static inline v16 v_sub(v16 a, v16 b) { v16 d = _mm512_sub_epi32(a, b); return _mm512_min_epu32(d, _mm512_add_epi32(d, VP)); }
+static inline v16 v_mul(v16 a, v16 b) {
+    v16 ao = _mm512_srli_epi64(a, 32), bo = _mm512_srli_epi64(b, 32);
+    v16 pe = _mm512_mul_epu32(a, b), po = _mm512_mul_epu32(ao, bo);
+    v16 qe = _mm512_mul_epu32(pe, VMU), qo = _mm512_mul_epu32(po, VMU);
+    v16 qpe = _mm512_mul_epu32(qe, VP), qpo = _mm512_mul_epu32(qo, VP);
+    v16 hi = _mm512_mask_blend_epi32(0xAAAA, _mm512_srli_epi64(pe, 32), po);
+    v16 qh = _mm512_mask_blend_epi32(0xAAAA, _mm512_srli_epi64(qpe, 32), qpo);
+    v16 t = _mm512_sub_epi32(hi, qh);
+    return _mm512_min_epu32(t, _mm512_add_epi32(t, VP));
+}
+static inline v16 v_sbox7(v16 x) { v16 x2 = v_mul(x, x), x3 = v_mul(x2, x), x4 = v_mul(x2, x2); return v_mul(x3, x4); }
+static inline void v_mds_light(v16* s) {
+    for (int c = 0; c < 16; c += 4) {
+        v16 a = s[c], b = s[c + 1], cc = s[c + 2], d = s[c + 3];
+        v16 t = v_add(v_add(a, b), v_add(cc, d));
+        s[c] = v_add(v_add(t, a), v_add(b, b));
+        s[c + 1] = v_add(v_add(t, b), v_add(cc, cc));
+        s[c + 2] = v_add(v_add(t, cc), v_add(d, d));
+        s[c + 3] = v_add(v_add(t, d), v_add(a, a));
+    }
+    for (int k = 0; k < 4; k++) {
+        v16 t = v_add(v_add(s[k], s[4 + k]), v_add(s[8 + k], s[12 + k]));
+        for (int j = 0; j < 16; j += 4) s[j + k] = v_add(s[j + k], t);
+    }
+}
+/* 16 independent permutations, lane l of s[i] = element i of state l */
+static void v_permute(v16* s) {
+    v_mds_light(s);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 16; i++) s[i] = v_sbox7(v_add(s[i], _mm512_set1_epi32((int)RC[16 * r + i])));
+        v_mds_light(s);
+    }
+    for (int r = 0; r < 13; r++) {
+        s[0] = v_sbox7(v_add(s[0], _mm512_set1_epi32((int)RC[64 + r])));
+        v16 t = s[0];
+        for (int i = 1; i < 16; i++) t = v_add(t, s[i]);
+        for (int i = 0; i < 16; i++) s[i] = v_add(t, v_mul(_mm512_set1_epi32((int)DIAG[i]), s[i]));
+    }
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 16; i++) s[i] = v_sbox7(v_add(s[i], _mm512_set1_epi32((int)RC[77 + 16 * r + i])));
+        v_mds_light(s);
+    }
+}
+int orc_fast_available(void) { return 1; }
+
+/* leaf digests of one matrix, 16 rows per permutation (rows % 16 == 0) */
+static void fast_hash_rows(const u32* mat, u64 rows, u64 width, u32* out) {
+    const v16 lane = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+#pragma omp parallel for schedule(static)
+    for (u64 r0 = 0; r0 < rows; r0 += 16) {
+        v16 st[16];
+        for (int i = 0; i < 16; i++) st[i] = _mm512_setzero_si512();
+        const v16 idx = _mm512_mullo_epi32(lane, _mm512_set1_epi32((int)width));
+        const u32* base = mat + r0 * width;
+        int fill = 0;
+        for (u64 c = 0; c < width; c++) {
+            st[fill++] = _mm512_i32gather_epi32(idx, (const int*)(base + c), 4);
+            if (fill == 8) { v_permute(st); fill = 0; }
+        }
+        if (fill) v_permute(st);
+        const v16 oidx = _mm512_slli_epi32(lane, 3);
+        for (int j = 0; j < 8; j++) _mm512_i32scatter_epi32((int*)(out + 8 * r0 + j), oidx, st[j], 4);
+    }
+}
+/* next[i] = compress(prev[2i], prev[2i+1]), 16 nodes per permutation (n % 16 == 0) */
+static void fast_compress_layer(const u32* prev, u32* next, u64 n) {
+    const v16 lane = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    const v16 iidx = _mm512_slli_epi32(lane, 4), oidx = _mm512_slli_epi32(lane, 3);
+#pragma omp parallel for schedule(static)
+    for (u64 i0 = 0; i0 < n; i0 += 16) {
+        v16 st[16];
+        for (int j = 0; j < 16; j++) st[j] = _mm512_i32gather_epi32(iidx, (const int*)(prev + 16 * i0 + j), 4);
+        v_permute(st);
+        for (int j = 0; j < 8; j++) _mm512_i32scatter_epi32((int*)(next + 8 * i0 + j), oidx, st[j], 4);
+    }
+}
+/* MerkleTreeMmcs commit of ONE matrix (the bench shape); digests_out as orc_merkle_commit */
+int orc_fast_merkle_commit_single(const u32* mat, u64 rows, u64 width, u32* digests_out, u32* root_out) {
+    orc_init();
+    if (!rows || (rows & (rows - 1))) return -1;
+    u32* layer = digests_out;
+    if (rows >= 16) fast_hash_rows(mat, rows, width, layer);
+    else orc_hash_rows(mat, rows, width, layer);
+    for (u64 len = rows; len > 1; len >>= 1) {
+        u32* next = layer + 8 * len;
+        if (len / 2 >= 16) fast_compress_layer(layer, next, len / 2);
+        else orc_compress_pairs(layer, next, len / 2);
+        layer = next;
+    }
+    memcpy(root_out, layer, 32);
+    return 0;
+}
+
+/* ---- vectorised DIF over rows (natural in, bit-reversed out), width % 16 == 0 */
+static inline void v_bfly(u32* x, u32* y, u64 width, u32 w) {
+    const v16 vw = _mm512_set1_epi32((int)w);
+    for (u64 c = 0; c < width; c += 16) {
+        v16 u = _mm512_loadu_si512(x + c), v = _mm512_loadu_si512(y + c);
+        _mm512_storeu_si512(x + c, v_add(u, v));
+        _mm512_storeu_si512(y + c, v_mul(v_sub(u, v), vw));
+    }
+}
+static inline void v_bfly_notw(u32* x, u32* y, u64 width) {
+    for (u64 c = 0; c < width; c += 16) {
+        v16 u = _mm512_loadu_si512(x + c), v = _mm512_loadu_si512(y + c);
+        _mm512_storeu_si512(x + c, v_add(u, v));
+        _mm512_storeu_si512(y + c, v_sub(u, v));
+    }
+}
+/* stages s and s+1 in one sweep: rows j, j+q, j+2q, j+3q of a block of 4q rows */
+static inline void v_bfly4(u32* r0, u32* r1, u32* r2, u32* r3, u64 width, u32 wa, u32 wb, u32 wc) {
+    const v16 va = _mm512_set1_epi32((int)wa), vb = _mm512_set1_epi32((int)wb), vc = _mm512_set1_epi32((int)wc);
+    for (u64 c = 0; c < width; c += 16) {
+        v16 x0 = _mm512_loadu_si512(r0 + c), x1 = _mm512_loadu_si512(r1 + c), x2 = _mm512_loadu_si512(r2 + c), x3 = _mm512_loadu_si512(r3 + c);
+        v16 a0 = v_add(x0, x2), a2 = v_mul(v_sub(x0, x2), va);   /* stage s: pairs (0,2), (1,3) */
+        v16 a1 = v_add(x1, x3), a3 = v_mul(v_sub(x1, x3), vb);
+        _mm512_storeu_si512(r0 + c, v_add(a0, a1));               /* stage s+1: pairs (0,1), (2,3), same twiddle */
+        _mm512_storeu_si512(r1 + c, v_mul(v_sub(a0, a1), vc));
+        _mm512_storeu_si512(r2 + c, v_add(a2, a3));
+        _mm512_storeu_si512(r3 + c, v_mul(v_sub(a2, a3), vc));
+    }
+}
+static void fast_dif_rows(u32* a, u64 n, u64 width, u32 root) {
+    u32 lg = 0; while ((1ull << lg) < n) lg++;
+    u32* tw = malloc(sizeof(u32) * (n / 2 + 1));
+    tw[0] = R_MOD_P;
+    for (u64 i = 1; i < n / 2; i++) tw[i] = bb_mul(tw[i - 1], root);
+    /* rows of a cache-resident block: ~512 KB */
+    u32 blk_lg = 1; while (blk_lg < lg && ((4ull * width) << (blk_lg + 1)) <= (512u << 10)) blk_lg++;
+    if (blk_lg > lg) blk_lg = lg;
+    u32 s = 0;
+    const u32 global = lg - blk_lg;
+    for (; s + 1 < global || (s < global && ((global - s) & 1) == 0 && s + 1 < lg); s += 2) { /* two global stages per sweep */
+        if (s + 1 >= lg) break;
+        const u64 q = n >> (s + 2), nblk = 1ull << s;
+#pragma omp parallel for collapse(2) schedule(static)
+        for (u64 b = 0; b < nblk; b++)
+            for (u64 j = 0; j < q; j++) {
+                u32* r0 = a + (b * 4 * q + j) * width;
+                v_bfly4(r0, r0 + q * width, r0 + 2 * q * width, r0 + 3 * q * width, width, tw[j << s], tw[(j + q) << s], tw[j << (s + 1)]);
+            }
+    }
+    for (; s < global; s++) { /* an odd global stage left over */
+        const u64 m = n >> (s + 1), nblk = 1ull << s;
+#pragma omp parallel for collapse(2) schedule(static)
+        for (u64 b = 0; b < nblk; b++)
+            for (u64 j = 0; j < m; j++) { u32* x = a + (b * 2 * m + j) * width; v_bfly(x, x + m * width, width, tw[j << s]); }
+    }
+    /* the remaining stages stay inside blocks of n >> s rows: one sweep, block by block */
+    if (s < lg) {
+        const u64 brows = n >> s, nb = 1ull << s;
+        const u32 s_first = s;
+#pragma omp parallel for schedule(static)
+        for (u64 b = 0; b < nb; b++) {
+            u32* base = a + b * brows * width;
+            for (u32 t = s_first; t < lg; t++) {
+                const u64 m = n >> (t + 1), inner = brows / (2 * m);
+                for (u64 ib = 0; ib < inner; ib++)
+                    for (u64 j = 0; j < m; j++) {
+                        u32* x = base + (ib * 2 * m + j) * width;
+                        if (t + 1 == lg) v_bfly_notw(x, x + m * width, width);
+                        else v_bfly(x, x + m * width, width, tw[j << t]);
+                    }
+            }
+        }
+    }
+    free(tw);
+}
+static inline void v_scale_row(const u32* src, u32* dst, u64 width, u32 f) {
+    const v16 vf = _mm512_set1_epi32((int)f);
+    for (u64 c = 0; c < width; c += 16) _mm512_storeu_si512(dst + c, v_mul(_mm512_loadu_si512(src + c), vf));
+}
+/* coset_lde_batch with bit-reversed output (width % 16 == 0, n >= 2): iDFT once, then per coset block c of the output the
+ * size-n DFT of coef[k] * (shift * w'^bitrev(c))^k / n -- the zero-padded stages of the size-(n << added_bits) transform
+ * are never executed (bit-identical result; tests compare with orc_coset_lde_batch) */
+int orc_fast_coset_lde_batch(const u32* evals, u64 n, u64 width, u32 added_bits, u32 shift, u32* out) {
+    orc_init();
+    if (width % 16 || n < 2 || (n & (n - 1))) return -1;
+    u32 lg = 0; while ((1ull << lg) < n) lg++;
+    u32* t = malloc(4 * n * width);
+    if (!t) return -2;
+    memcpy(t, evals, 4 * n * width);
+    fast_dif_rows(t, n, width, bb_inv(orc_two_adic_generator(lg)));   /* bit-reversed coefficients, unscaled */
+    const u32 ninv = bb_inv(bb_to_monty((u32)(n % P)));
+    const u32 wprime = orc_two_adic_generator(lg + added_bits);
+    for (u64 c = 0; c < (1ull << added_bits); c++) {
+        u32* blk = out + c * n * width;
+        const u32 g = bb_mul(shift, bb_pow(wprime, bitrev32((u32)c, added_bits)));
+#pragma omp parallel
+        {
+            /* each thread walks a contiguous range of k with a running power */
+            int nt = 1, id = 0;
+#ifdef _OPENMP
+            nt = omp_get_num_threads(); id = omp_get_thread_num();
+#endif
+            u64 k0 = n * (u64)id / nt, k1 = n * (u64)(id + 1) / nt;
+            u32 f = bb_mul(ninv, bb_pow(g, k0));
+            for (u64 k = k0; k < k1; k++) { v_scale_row(t + (u64)bitrev32((u32)k, lg) * width, blk + k * width, width, f); f = bb_mul(f, g); }
+        }
+        fast_dif_rows(blk, n, width, orc_two_adic_generator(lg));
+    }
+    free(t);
+    return 0;
+}
+#else
+int orc_fast_available(void) { return 0; }
+int orc_fast_merkle_commit_single(const u32* mat, u64 rows, u64 width, u32* digests_out, u32* root_out) {
+    const u32* m[1] = {mat};
+    return orc_merkle_commit(m, &rows, &width, 1, digests_out, root_out);
+}
+int orc_fast_coset_lde_batch(const u32* evals, u64 n, u64 width, u32 added_bits, u32 shift, u32* out) {
+    orc_coset_lde_batch(evals, n, width, added_bits, shift, 1, out);
+    return 0;
+}
+#endif
+
+/* column extraction of the synthetic matrix without materialising it: out[i] = fill value at index offset + i * stride */
+void orc_fill_strided(u32* out, u64 n, u64 seed, u64 offset, u64 stride) {
+#pragma omp parallel for schedule(static)
+    for (u64 i = 0; i < n; i++) out[i] = (u32)(splitmix64(seed ^ (offset + i * stride)) % P);
+}
+/* Horner evaluation of one polynomial (n Montgomery coefficients, natural order) at cnt points: the definition-level
+ * check of an LDE entry, independent of any fast transform */
+void orc_eval_poly_many(const u32* coef, u64 n, const u32* xs, u64 cnt, u32* out) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (u64 k = 0; k < cnt; k++) {
+        u32 acc = 0, x = xs[k];
+        for (u64 j = n; j-- > 0;) acc = bb_add(bb_mul(acc, x), coef[j]);
+        out[k] = acc;
+    }
 }

@@ -57,6 +57,11 @@ def _load(native: bool = False):
         "orc_fri_commit_phase": (C.c_uint32, [_u32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, _u32p, _u32p, _u32p]),
         "orc_fill": (None, [_u32p, C.c_uint64, C.c_uint64, C.c_uint64]),
         "orc_checksum": (C.c_uint64, [_u32p, C.c_uint64, C.c_uint64]),
+        "orc_fast_available": (C.c_int, []),
+        "orc_fast_merkle_commit_single": (C.c_int, [_u32p, C.c_uint64, C.c_uint64, _u32p, _u32p]),
+        "orc_fast_coset_lde_batch": (C.c_int, [_u32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _u32p]),
+        "orc_fill_strided": (None, [_u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+        "orc_eval_poly_many": (None, [_u32p, C.c_uint64, _u32p, C.c_uint64, _u32p]),
     }
     for k, (res, args) in sig.items():
         f = getattr(lib, k)
@@ -68,8 +73,13 @@ _LIB = None
 _NATIVE = False
 
 
-def lib(native: bool = False):
+def lib(native=None):
+    """the loaded oracle library; native=None keeps the current flavour (portable x86-64-v3 build unless use_native(True)
+    selected the -march=native one).  r01 bug: the default argument was False, so every plain wrapper call silently switched
+    a native selection back to the portable build."""
     global _LIB, _NATIVE
+    if native is None:
+        native = _NATIVE
     if _LIB is None or native != _NATIVE:
         _LIB, _NATIVE = _load(native), native
     return _LIB
@@ -276,6 +286,45 @@ def fri_commit_phase(vec, log_blowup, log_final_poly_len, betas=None, challenger
 def fill(n, seed, offset=0):
     out = np.zeros(n, np.uint32)
     lib().orc_fill(out, n, seed, offset)
+    return out
+
+
+def fast_available() -> bool:
+    """True when the loaded library was compiled with the AVX-512 fast path (`make native` on an AVX-512 host)"""
+    return bool(lib().orc_fast_available())
+
+
+def fast_coset_lde_batch(evals, added_bits, shift):
+    """bench.py CPU baseline: coset_lde_batch with bit-reversed rows through the vectorised path (scalar fallback inside)"""
+    evals = np.ascontiguousarray(evals, dtype=np.uint32)
+    out = np.zeros((evals.shape[0] << added_bits, evals.shape[1]), np.uint32)
+    if lib().orc_fast_coset_lde_batch(evals, evals.shape[0], evals.shape[1], added_bits, shift, out) != 0:
+        lib().orc_coset_lde_batch(evals, evals.shape[0], evals.shape[1], added_bits, shift, 1, out)
+    return out
+
+
+def fast_merkle_commit_single(mat):
+    mat = np.ascontiguousarray(mat, dtype=np.uint32)
+    dig = np.zeros((2 * mat.shape[0] - 1, 8), np.uint32)
+    root = np.zeros(8, np.uint32)
+    if lib().orc_fast_merkle_commit_single(mat, mat.shape[0], mat.shape[1], dig, root) != 0:
+        raise ValueError("bad shape")
+    return root, dig
+
+
+def fill_column(rows, width, col, seed):
+    """column `col` of the rows x width matrix fill(rows * width, seed) would produce, without building the matrix"""
+    out = np.zeros(rows, np.uint32)
+    lib().orc_fill_strided(out, rows, seed, col, width)
+    return out
+
+
+def eval_poly_many(coef, xs):
+    """Horner: the polynomial with Montgomery coefficients `coef` (natural order) at every point of `xs`"""
+    coef = np.ascontiguousarray(coef, dtype=np.uint32).reshape(-1)
+    xs = np.ascontiguousarray(xs, dtype=np.uint32).reshape(-1)
+    out = np.zeros(xs.size, np.uint32)
+    lib().orc_eval_poly_many(coef, coef.size, xs, xs.size, out)
     return out
 
 

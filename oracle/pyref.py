@@ -340,12 +340,16 @@ class DuplexChallenger:
         return self.sample() & ((1 << bits) - 1)
 
     def check_witness(self, bits, w):
+        if bits == 0:   # p3-challenger 0.4.3: no proof of work requested, transcript untouched
+            return True
         self.observe(w)
         return self.sample_bits(bits) == 0
 
     def grind(self, bits):
         """Smallest witness (the reference uses a parallel find_any, so its witness is not
         deterministic; the smallest one is always among the valid answers)."""
+        if bits == 0:
+            return 0
         w = 0
         while True:
             if self.clone().check_witness(bits, w):

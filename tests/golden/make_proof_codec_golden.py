@@ -32,7 +32,7 @@ for path in sorted(glob.glob(os.path.join(REF, "*-proof-*.json"))):
         "public_values_sha256": hashlib.sha256(pv).hexdigest(), "n_public_values": int(v.public_values.size),
         "n_proofs": len(v.proofs), "n_airs": len(p.per_air), "degrees": [a.degree for a in p.per_air],
         "n_main_commits": len(p.main_trace_commits), "fri_rounds": len(p.fri.commit_phase_commits),
-        "n_queries": len(p.fri.query_proofs), "final_poly_len": len(p.fri.final_poly), "pow_witness": p.fri.pow_witness,
+        "n_queries": len(p.fri.query_proofs), "final_poly_len": len(p.fri.final_poly), "pow_witness": p.fri.pow_witness, "pow_witness_wire": int(W.monty_scalar(p.fri.pow_witness)),
         "quotient_commit": p.quotient_commit.tolist(), "has_logup_pow": p.logup_pow_witness is not None,
     }
     print(name, "ok:", len(blob), "bytes,", len(p.per_air), "AIRs,", len(p.fri.query_proofs), "queries")

@@ -325,3 +325,44 @@ def test_open_phase_primitives_definitions():
         nat[R.bitrev(i, m.bit_length() - 1)] = ro[i]
     co = O.from_monty(O.dft_batch(nat, shift=shift_m, inverse=True))
     assert not co[n - 1:].any() and co[: n - 1].any()
+
+
+def test_avx512_fast_path_matches_scalar_restatement():
+    """bench.py's CPU baseline uses the AVX-512 path of the oracle (packed Poseidon2, vectorised butterflies) when the host
+    has AVX-512; it must equal the scalar restatement (the parity checker) bit for bit."""
+    try:
+        O.build(native=True)
+        O.use_native(True)
+        if not O.fast_available():
+            pytest.skip("host CPU has no AVX-512: the fast path is not compiled in")
+        rng = np.random.default_rng(512)
+        shift = int(O.to_monty([31])[0])
+        for n, w in [(1, 16), (4, 16), (9, 32), (12, 64), (13, 48), (15, 256)]:
+            m = rng.integers(0, P, (1 << n, w), dtype=np.uint64).astype(np.uint32)
+            for ab in (1, 2):
+                ref = O.coset_lde_batch(m, ab, shift, bitrev_out=True)
+                assert np.array_equal(O.fast_coset_lde_batch(m, ab, shift), ref), (n, w, ab)
+            r1, layers = O.merkle_commit([ref])
+            r2, dig = O.fast_merkle_commit_single(ref)
+            assert np.array_equal(r1, r2) and np.array_equal(np.concatenate(layers), dig), (n, w)
+        # widths the vector path does not take fall back to the scalar code inside the same entry points
+        m = rng.integers(0, P, (64, 9), dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(O.fast_coset_lde_batch(m, 1, shift), O.coset_lde_batch(m, 1, shift, bitrev_out=True))
+        r1, _ = O.merkle_commit([m])
+        r2, _ = O.fast_merkle_commit_single(m)
+        assert np.array_equal(r1, r2)
+    finally:
+        O.use_native(False)
+
+
+def test_horner_and_column_helpers():
+    """oracle helpers used by the headline GPU tests: a column of the synthetic matrix, and Horner evaluation == DFT entry"""
+    n, w, seed = 6, 5, 77
+    full = O.fill((1 << n) * w, seed).reshape(1 << n, w)
+    for c in range(w):
+        assert np.array_equal(O.fill_column(1 << n, w, c, seed), full[:, c])
+    col = full[:, 2].reshape(-1, 1)
+    coef = O.dft_batch(col, inverse=True).reshape(-1)
+    g = O.two_adic_generator(n)
+    xs = np.array([O.lib().orc_pow(g, i) for i in range(1 << n)], np.uint32)
+    assert np.array_equal(O.eval_poly_many(coef, xs), col.reshape(-1))

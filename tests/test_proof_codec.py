@@ -105,6 +105,12 @@ def test_reference_fixtures_reencode_byte_identically():
         p = v.proofs[0]
         assert [a.degree for a in p.per_air] == g["degrees"] and len(p.fri.query_proofs) == g["n_queries"]
         assert p.fri.pow_witness == g["pow_witness"] and p.quotient_commit.tolist() == g["quotient_commit"]
+        # the wire word is the Montgomery form of the witness (a canonical integer on the wire makes a p3 verifier
+        # observe a different element).  Evidence from the fixtures themselves: p3's grind searches 0..p with rayon, whose
+        # range splits start at multiples of p / 2^k, and with 16 PoW bits a hit comes after ~2^16 tries -- the CANONICAL value
+        # decoded this way sits a few ten thousand above such a split point in every fixture, the raw word does not.
+        assert W.monty_scalar(p.fri.pow_witness) == g["pow_witness_wire"]
+        assert ((p.fri.pow_witness * 2048) % W.P_MOD) // 2048 < (1 << 17), "canonical witness is not just above a rayon split point"
         # structure implied by the FRI parameters: round r opens a tree of height log_max - 1 - r
         log_max = max(g["degrees"]).bit_length() - 1 + 2
         for qp in p.fri.query_proofs:

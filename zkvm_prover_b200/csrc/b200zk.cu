@@ -186,9 +186,18 @@ inline size_t hi_words(uint64_t n_entries) { return (size_t)std::max<uint64_t>(n
 int ensure_roots(b200zk_ctx* ctx, int n) {
     if (ctx->tw_lo[n]) return B200ZK_OK;
     uint64_t N = 1ull << n;
-    TRY(dev_alloc(ctx, lo_words(N) * 4, (void**)&ctx->tw_lo[n]));
-    TRY(dev_alloc(ctx, hi_words(N) * 4, (void**)&ctx->tw_hi[n]));
-    return pow_tables(ctx, ctx->tw_lo[n], ctx->tw_hi[n], bb::two_adic_generator(n), bb::ONE, N);
+    uint32_t *lo = nullptr, *hi = nullptr;  // published only when both tables exist and the generating kernel was enqueued
+    TRY(dev_alloc(ctx, lo_words(N) * 4, (void**)&lo));
+    int rc = dev_alloc(ctx, hi_words(N) * 4, (void**)&hi);
+    if (rc == B200ZK_OK) rc = pow_tables(ctx, lo, hi, bb::two_adic_generator(n), bb::ONE, N);
+    if (rc != B200ZK_OK) {
+        dev_free(ctx, lo);
+        dev_free(ctx, hi);
+        return rc;
+    }
+    ctx->tw_lo[n] = lo;
+    ctx->tw_hi[n] = hi;
+    return B200ZK_OK;
 }
 int ensure_local(b200zk_ctx* ctx, int inverse, int K) {
     if (ctx->tw_local[inverse][K]) return B200ZK_OK;
@@ -244,9 +253,56 @@ int make_natural_map(b200zk_ctx* ctx, const uint32_t* base, uint32_t width, uint
     return B200ZK_OK;
 }
 
+// dynamic shared memory of pass_kernel_tma: barriers | STAGES tiles | local roots | {prescale, twist} row factors
+inline size_t tma_smem_bytes(int K, uint32_t tcols) {
+    const size_t R = (size_t)1 << K;
+    return 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (2 * std::max<size_t>(R / 2, 1) + 4 * R) * 4;
+}
+
+// B200ZK_NTT_TRACE=1: synchronise around every pass and print its time (experiments only; serialises the stream)
+bool ntt_trace() {
+    static const int v = [] {
+        const char* e = getenv("B200ZK_NTT_TRACE");
+        return e ? atoi(e) : 0;
+    }();
+    return v != 0;
+}
+struct PassTimer {
+    b200zk_ctx* ctx;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const char* what;
+    int n, s0, K;
+    uint32_t width;
+    PassTimer(b200zk_ctx* c, const char* w, int n_, int s0_, int K_, uint32_t width_) : ctx(c), what(w), n(n_), s0(s0_), K(K_), width(width_) {
+        if (!ntt_trace()) return;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~PassTimer() {
+        if (!e0) return;
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = 8.0 * (double)(1ull << n) * width;
+        fprintf(stderr, "[ntt] %-10s n=%d s0=%2d K=%d width=%u  %.3f ms  %.0f GB/s (read+write)\n", what, n, s0, K, width, ms, bytes / ms / 1e6);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+};
+
 bool tma_enabled() {
     static const int v = [] {
         const char* e = getenv("B200ZK_NTT_TMA");  // experiment knob: 0 forces the plain pass kernel
+        return e ? atoi(e) : 1;
+    }();
+    return v != 0;
+}
+
+bool direct_enabled() {
+    static const int v = [] {
+        const char* e = getenv("B200ZK_NTT_DIRECT");  // experiment knob: 0 keeps every pass on the TMA ring kernel
         return e ? atoi(e) : 1;
     }();
     return v != 0;
@@ -309,12 +365,35 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         p.post_lo = last ? post.lo : nullptr;
         p.post_hi = last ? post.hi : nullptr;
         p.out_natural = last ? out_natural : 0;
+        if (p.out_natural && p.in == p.out) return fail(ctx, B200ZK_ERR_ARG, "internal: a natural-order (scattering) pass cannot run in place");
         p.rt_base = 0;
         {
             const char* e = getenv("B200ZK_NTT_PREFETCH");  // experiment knob: CTAs of look-ahead (0 disables)
             p.prefetch_dist = e ? (uint32_t)atoi(e) : 148u; // measured best look-ahead (profiles/ntt_tuning_r01.txt)
         }
         const uint64_t R = 1ull << K;
+        // Passes that multiply by per-row factors (coset prescale, inter-pass twist: every pass but the last one of a
+        // transform) run on the direct kernel, which computes the factor tables under its own global loads (B200, LDE
+        // 2^23 x 256: 4.75 / 4.55 / 5.2 ms per pass against 5.0 / 4.9 / 6.3 ms on the TMA ring); the factor-free last pass
+        // stays on the TMA ring (3.8 against 4.1-4.4 ms).  profiles/ntt_lab_r02.txt
+        const bool has_factors = p.pre_lo != nullptr || (n - s0 - K) > 0;
+        if (tma_ok && direct_enabled() && has_factors && K >= 6 && K <= 8 && !p.post_lo && !(last && scatter)) {
+            // direct pass: 2^13-element tiles, first round from global memory, last round to global memory (ntt.cuh)
+            const int lcd = 13 - K;
+            p.lc = lcd;
+            const uint64_t tiles = ((1ull << n) >> K) * ((width + (1u << lcd) - 1) >> lcd);
+            if (tiles > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
+            const size_t dsm = ((size_t)R << lcd) * 4 + (R / 2) * 8 + 2 * R * 8;
+            {
+                PassTimer tm(ctx, inverse ? (p.out_natural ? "inv-scat" : "inv") : (p.pre_lo ? "fwd-pre" : "fwd"), n, s0, K, width);
+                if (K == 8) ntt::pass_kernel_direct<8, 5><<<(uint32_t)tiles, ntt::DIRECT_THREADS, dsm, ctx->stream>>>(p);
+                else if (K == 7) ntt::pass_kernel_direct<7, 6><<<(uint32_t)tiles, ntt::DIRECT_THREADS, dsm, ctx->stream>>>(p);
+                else ntt::pass_kernel_direct<6, 7><<<(uint32_t)tiles, ntt::DIRECT_THREADS, dsm, ctx->stream>>>(p);
+            }
+            LAUNCHED();
+            s0 += K;
+            continue;
+        }
         if (tma_ok && K <= ntt::TMA_MAX_K && !p.post_lo) {
             // persistent warp-specialised TMA pass: 2^13-element tiles, 3-stage ring, 2 CTAs per SM
             int tl = std::min(ntt::TMA_TILE_LOG - K, ntt::MAX_TILE_COLS_LOG);
@@ -329,7 +408,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
                 // one launch per destination: the row tiles [rt0, rt1) of this pass are the rows of one owner (L = 0 here)
                 const uint64_t R2 = 1ull << K, rows = 1ull << n;
                 if (scatter->mg % R2) return fail(ctx, B200ZK_ERR_SHAPE, "row block smaller than a tile");
-                const size_t tsm2 = 128 + (size_t)ntt::TMA_STAGES * (R2 * tcols * 4) + (2 * std::max<uint64_t>(R2 / 2, 1) + 4 * R2) * 4;
+                const size_t tsm2 = tma_smem_bytes(K, tcols);
                 for (uint64_t g = scatter->g0; g < scatter->g0 + rows;) {
                     const uint64_t r = g / scatter->mg;
                     const uint64_t g_end = std::min(scatter->g0 + rows, (r + 1) * scatter->mg);
@@ -350,9 +429,12 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             if (p.out_natural) TRY(make_natural_map(ctx, p.out, width, p.out_pitch, n, K, tl, &out_map));
             else TRY(make_pass_map(ctx, p.out, width, p.out_pitch, n, s0, K, tl, &out_map));
             // (dynamic shared memory limits are raised once per device in configure_kernels)
-            const size_t tsm = 128 + (size_t)ntt::TMA_STAGES * (R * tcols * 4) + (2 * std::max<uint64_t>(R / 2, 1) + 4 * R) * 4;
+            const size_t tsm = tma_smem_bytes(K, tcols);
             const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)NTT_TMA_CTAS * ctx->num_sms);
-            ntt::pass_kernel_tma<<<grid, ntt::TMA_THREADS, tsm, ctx->stream>>>(in_map, out_map, p, (uint32_t)tiles);
+            {
+                PassTimer tm(ctx, inverse ? (p.out_natural ? "inv-scat" : "inv") : (p.pre_lo ? "fwd-pre" : "fwd"), n, s0, K, width);
+                ntt::pass_kernel_tma<<<grid, ntt::TMA_THREADS, tsm, ctx->stream>>>(in_map, out_map, p, (uint32_t)tiles);
+            }
             LAUNCHED();
             s0 += K;
             continue;
@@ -417,10 +499,11 @@ const char* b200zk_version(void) { return "b200zk 0.1 (sm_100a)"; }
 // host thread) can only ever write the same value and no launch depends on a value another thread may be changing.
 static int configure_kernels(int max_smem_optin) {
     const void* big[] = {(const void*)ntt::pass_kernel_tma, (const void*)ntt::pass_kernel<4>, (const void*)ntt::pass_kernel<1>,
+                         (const void*)ntt::pass_kernel_direct<8, 5>, (const void*)ntt::pass_kernel_direct<7, 6>, (const void*)ntt::pass_kernel_direct<6, 7>,
                          (const void*)op::dot_ext_powers_kernel<4>, (const void*)op::dot_ext_powers_kernel<1>};
     for (const void* f : big)
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return B200ZK_ERR_CUDA;
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 6; i++)
         if (cudaFuncSetAttribute(big[i], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) return B200ZK_ERR_CUDA;
     return B200ZK_OK;
 }
@@ -770,10 +853,13 @@ int b200zk_dft_batch(b200zk_ctx* ctx, const b200zk_mat* in, uint32_t shift, int 
         post = Scale{ctx->tab, ctx->tab + lo_words(N)};
     }
     const bool natural = !bitrev_rows;
-    const bool multi = make_plan(n).size() > 1;
+    // Whether the transform takes more than one pass depends on the plan run_transform picks (the TMA plan cuts at 8 stages,
+    // the plain one at 9/10), so every natural-order transform with more than one stage gets its own work buffer: the
+    // scattering last pass must never run in place (r01 advice: n = 9 was planned [9] here and [5,4] there).
+    const bool multi = n > 1;
     b200zk_mat* tmp = nullptr;
     uint32_t* work = (*out)->d;
-    if (rc == B200ZK_OK && natural && multi) {  // the scattering last pass must not run in place
+    if (rc == B200ZK_OK && natural && multi) {
         rc = b200zk_mat_alloc(ctx, N, W, &tmp);
         if (rc == B200ZK_OK) work = tmp->d;
     }
@@ -823,15 +909,33 @@ int b200zk_poseidon2_permute(b200zk_ctx* ctx, uint32_t* h_states, uint64_t n) {
     return rc;
 }
 
-static int make_group(b200zk_ctx* ctx, b200zk_mat* const* mats, const uint32_t* idx, uint32_t cnt, mk::Group* g) {
-    if (cnt > (uint32_t)mk::MAX_GROUP) return fail(ctx, B200ZK_ERR_SHAPE, "more than 128 matrices of one height in a commit");
+// Descriptors of the matrices hashed into one sponge.  Up to MAX_GROUP of them travel as a kernel parameter; more (p3's
+// MerkleTreeMmcs has no limit on matrices per height) go through a device array, returned in *d_ext for the caller to
+// release with dev_free once the kernel that reads it has been enqueued (release is stream ordered).
+static int make_group(b200zk_ctx* ctx, b200zk_mat* const* mats, const uint32_t* idx, uint32_t cnt, mk::Group* g, void** d_ext) {
+    *d_ext = nullptr;
     g->n = (int)cnt;
     g->fast8 = cnt > 0;
+    g->ext = nullptr;
+    std::vector<mk::MatRef> big;
+    if (cnt > (uint32_t)mk::MAX_GROUP) big.resize(cnt);
     for (uint32_t i = 0; i < cnt; i++) {
         const b200zk_mat* m = mats[idx[i]];
-        g->m[i].ptr = m->d;
-        g->m[i].width = m->width;
+        mk::MatRef& r = big.empty() ? g->m[i] : big[i];
+        r.ptr = m->d;
+        r.width = m->width;
         if (m->width % 8 != 0 || ((uintptr_t)m->d % 32) != 0) g->fast8 = 0;
+    }
+    if (!big.empty()) {
+        TRY(dev_alloc(ctx, big.size() * sizeof(mk::MatRef), d_ext));
+        // pageable source: the runtime stages it before returning, so `big` may go out of scope
+        cudaError_t e = cudaMemcpyAsync(*d_ext, big.data(), big.size() * sizeof(mk::MatRef), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            dev_free(ctx, *d_ext);
+            *d_ext = nullptr;
+            return fail(ctx, B200ZK_ERR_CUDA, std::string("descriptor upload: ") + cudaGetErrorString(e));
+        }
+        g->ext = static_cast<const mk::MatRef*>(*d_ext);
     }
     return B200ZK_OK;
 }
@@ -843,9 +947,11 @@ int b200zk_hash_rows_dev(b200zk_ctx* ctx, const b200zk_mat* m, uint32_t* d_diges
     mk::Group g;
     b200zk_mat* one[1] = {const_cast<b200zk_mat*>(m)};
     uint32_t idx0 = 0;
-    TRY(make_group(ctx, one, &idx0, 1, &g));
+    void* d_ext = nullptr;
+    TRY(make_group(ctx, one, &idx0, 1, &g, &d_ext));
     if (g.fast8) mk::leaf_hash_fast_kernel<<<(uint32_t)((m->rows + 255) / 256), 256, 0, ctx->stream>>>(g, m->rows, d_digests);
     else mk::leaf_hash_kernel<<<(uint32_t)((m->rows + 255) / 256), 256, 0, ctx->stream>>>(g, m->rows, d_digests);
+    dev_free(ctx, d_ext);
     LAUNCHED();
     return B200ZK_OK;
 }
@@ -870,6 +976,7 @@ int b200zk_compress_pairs_dev(b200zk_ctx* ctx, const uint32_t* d_in, uint32_t* d
     mk::Group g;
     g.n = 0;
     g.fast8 = 0;
+    g.ext = nullptr;
     mk::compress_layer_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_out, n, g);
     LAUNCHED();
     return B200ZK_OK;
@@ -954,7 +1061,8 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
         uint32_t g0 = pos;
         while (pos < k && mats[order[pos]]->rows == t->max_h) pos++;
         mk::Group g;
-        rc = make_group(ctx, mats, order.data() + g0, pos - g0, &g);
+        void* d_ext = nullptr;
+        rc = make_group(ctx, mats, order.data() + g0, pos - g0, &g, &d_ext);
         if (rc == B200ZK_OK && leaf_fn) {
             rc = leaf_fn(ctx, leaf_user, t->d_digests);  // the caller produces layer 0 itself (strip pipeline)
         } else if (rc == B200ZK_OK) {
@@ -963,6 +1071,7 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
             ctx->launches++;
             if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "leaf_hash launch failed");
         }
+        dev_free(ctx, d_ext);
     }
     uint32_t layer = 0;
     for (uint64_t len = t->max_h; len > 1 && rc == B200ZK_OK; len >>= 1, layer++) {
@@ -978,11 +1087,13 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
         uint32_t g0 = pos;
         while (pos < k && mats[order[pos]]->rows == n_next) pos++;
         mk::Group g;
-        rc = make_group(ctx, mats, order.data() + g0, pos - g0, &g);
+        void* d_ext = nullptr;
+        rc = make_group(ctx, mats, order.data() + g0, pos - g0, &g, &d_ext);
         if (rc != B200ZK_OK) break;
         mk::compress_layer_kernel<<<(uint32_t)((n_next + 255) / 256), 256, 0, ctx->stream>>>(prev, next, n_next, g);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "compress_layer launch failed");
+        dev_free(ctx, d_ext);
     }
     if (rc == B200ZK_OK && pos != k) rc = fail(ctx, B200ZK_ERR_SHAPE, "matrix height not reached while building the tree");
     if (rc != B200ZK_OK) {
@@ -1030,6 +1141,7 @@ int b200zk_lde_commit(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uin
     // gathered side by side into a work matrix (pitch a multiple of 4), extended with full-width tiles, and the result is
     // scattered into each matrix's own tightly packed LDE (the Merkle leaves stay separate row-major matrices).
     std::vector<char> done(k, 0);
+    if (rc == B200ZK_OK && cudaSetDevice(ctx->device) != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "cudaSetDevice failed");
     for (uint32_t i = 0; i < k && rc == B200ZK_OK; i++) {
         if (done[i]) continue;
         std::vector<uint32_t> grp;
@@ -1057,7 +1169,6 @@ int b200zk_lde_commit(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uin
             done[i] = 1;
             continue;
         }
-        CU(cudaSetDevice(ctx->device));
         const int n = log2u(N);
         uint32_t *pin = nullptr, *pout = nullptr;
         rc = dev_alloc(ctx, N * wp * 4, (void**)&pin);
@@ -1122,29 +1233,40 @@ int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
         }
     }
     uint32_t *sbuf[2] = {nullptr, nullptr}, *cap = nullptr;
-    TRY(dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[0]));
-    TRY(dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[1]));
-    TRY(dev_alloc(ctx, M * 32, (void**)&cap));
-    TRY(lde_tables(ctx, n, j.added_bits, j.shift));
+    int rc = dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[0]);
+    if (rc == B200ZK_OK) rc = dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[1]);
+    if (rc == B200ZK_OK) rc = dev_alloc(ctx, M * 32, (void**)&cap);
+    if (rc == B200ZK_OK) rc = lde_tables(ctx, n, j.added_bits, j.shift);
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == B200ZK_OK) rc = fail(ctx, B200ZK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
     // the strip buffers come from the compute stream's pool: the copy stream may only touch them after this point
-    CU(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
-    CU(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
+    if (rc == B200ZK_OK) cuda_ok(cudaEventRecord(ctx->ev_consumed[0], ctx->stream), "event record");
+    if (rc == B200ZK_OK) cuda_ok(cudaEventRecord(ctx->ev_consumed[1], ctx->stream), "event record");
     const uint32_t strips = j.W / j.strip;
-    int rc = B200ZK_OK;
+    bool copies_in_flight = false;
     for (uint32_t s = 0; s < strips && rc == B200ZK_OK; s++) {
         const int b = s & 1;
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
-        CU(cudaMemcpy2DAsync(sbuf[b], (size_t)j.strip * 4, j.h_values + (size_t)s * j.strip, (size_t)j.W * 4, (size_t)j.strip * 4, j.N, cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
-        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+        if (!cuda_ok(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0), "stream wait")) break;
+        if (!cuda_ok(cudaMemcpy2DAsync(sbuf[b], (size_t)j.strip * 4, j.h_values + (size_t)s * j.strip, (size_t)j.W * 4, (size_t)j.strip * 4, j.N,
+                                       cudaMemcpyHostToDevice, ctx->copy_stream),
+                     "strip copy"))
+            break;
+        copies_in_flight = true;
+        if (!cuda_ok(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream), "event record")) break;
+        if (!cuda_ok(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0), "stream wait")) break;
         rc = lde_core(ctx, sbuf[b], j.strip, n, j.strip, j.added_bits, j.lde->d + (size_t)s * j.strip, j.W);
         if (rc != B200ZK_OK) break;
-        CU(cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+        if (!cuda_ok(cudaEventRecord(ctx->ev_consumed[b], ctx->stream), "event record")) break;
         mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, ctx->stream>>>(j.lde->d, j.W, s * j.strip, j.strip, M, cap, s == 0, s + 1 == strips,
                                                                                            d_digests);
-        LAUNCHED();
+        ctx->launches++;
+        cuda_ok(cudaGetLastError(), "leaf_absorb_strip launch");
     }
+    // on an error path copies from the caller's h_values may still be queued on the copy stream: drain it before the
+    // buffers go back to the allocator and before the caller is told it may release the host memory
+    if (rc != B200ZK_OK && copies_in_flight) cudaStreamSynchronize(ctx->copy_stream);
     dev_free(ctx, sbuf[0]);
     dev_free(ctx, sbuf[1]);
     dev_free(ctx, cap);
@@ -1411,6 +1533,10 @@ int b200zk_chal_sample_bits(b200zk_ctx* ctx, b200zk_chal* c, uint32_t bits, uint
 int b200zk_chal_grind(b200zk_ctx* ctx, b200zk_chal* c, uint32_t bits, uint32_t* h_witness) {
     if (!ctx) return B200ZK_ERR_ARG;
     if (!c || !h_witness || bits > 30) return fail(ctx, B200ZK_ERR_ARG, "bad grind request");
+    if (bits == 0) {  // p3-challenger 0.4.3 (the reference's pin, Cargo.lock:5576): no proof of work, the transcript is left untouched
+        *h_witness = 0;
+        return B200ZK_OK;
+    }
     uint32_t* best = ctx->d_small;
     uint32_t init = 0xffffffffu;
     CU(cudaMemcpyAsync(best, &init, 4, cudaMemcpyHostToDevice, ctx->stream));

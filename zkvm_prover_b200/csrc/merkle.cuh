@@ -17,7 +17,9 @@ struct Group {
     MatRef m[MAX_GROUP];
     int n;
     int fast8;  // every matrix: width % 8 == 0 and 32-byte aligned base  -> vector path
+    const MatRef* ext;  // n > MAX_GROUP (p3 has no limit on matrices per height): the descriptors live in device memory instead
 };
+__device__ __forceinline__ MatRef mref(const Group& g, int i) { return g.ext ? g.ext[i] : g.m[i]; }
 
 // row data is read through L1 (allocating): a thread consumes its 128-byte line in two 64-byte steps ~100 us apart, and
 // the per-SM working set (resident threads x 128 B <= 160 KB) fits the L1, so the second half never goes back to L2/HBM
@@ -43,8 +45,9 @@ struct Cursor {
 __device__ __forceinline__ void cursor_next_matrix(const Group& g, uint64_t row, Cursor& cur) {
     cur.m++;
     if (cur.m < g.n) {
-        cur.w = g.m[cur.m].width;
-        cur.p = g.m[cur.m].ptr + row * cur.w;
+        const MatRef r = mref(g, cur.m);
+        cur.w = r.width;
+        cur.p = r.ptr + row * cur.w;
         cur.c = 0;
     }
 }
@@ -82,8 +85,9 @@ __device__ __forceinline__ void sponge_rows(const Group& g, uint64_t row, uint32
         // refetched later (ncu r01: 47.7 GB of DRAM traffic for 17.7 GB of data).  Two permutations run per step
         // while the next 64 B are in flight.
         for (int m = 0; m < g.n; m++) {
-            const uint32_t w = g.m[m].width;
-            const uint4* p = reinterpret_cast<const uint4*>(g.m[m].ptr + row * w);
+            const MatRef r = mref(g, m);
+            const uint32_t w = r.width;
+            const uint4* p = reinterpret_cast<const uint4*>(r.ptr + row * w);
             const uint32_t chunks = w >> 3;  // 32-byte chunks in this row
             uint4 a = ldg_stream(p), b = ldg_stream(p + 1), c = a, d = b;
             if (chunks > 1) { c = ldg_stream(p + 2); d = ldg_stream(p + 3); }
@@ -112,8 +116,9 @@ __device__ __forceinline__ void sponge_rows(const Group& g, uint64_t row, uint32
     Cursor cur;
     cur.m = 0;
     cur.c = 0;
-    cur.w = g.m[0].width;
-    cur.p = g.m[0].ptr + row * cur.w;
+    const MatRef r0 = mref(g, 0);
+    cur.w = r0.width;
+    cur.p = r0.ptr + row * cur.w;
     uint32_t buf[8];
     int cnt = gather8(g, row, cur, buf);
     while (cnt > 0) {
@@ -158,8 +163,9 @@ __global__ void __launch_bounds__(256, MK_FAST_MINB) leaf_hash_fast_kernel(const
 #pragma unroll
     for (int k = 0; k < 16; k++) st[k] = 0;
     for (int m = 0; m < g.n; m++) {
-        const uint32_t w = g.m[m].width;
-        const uint4* p = reinterpret_cast<const uint4*>(g.m[m].ptr + i * w);
+        const MatRef r = mref(g, m);
+        const uint32_t w = r.width;
+        const uint4* p = reinterpret_cast<const uint4*>(r.ptr + i * w);
         const uint32_t chunks = w >> 3;
 #pragma unroll 1
         for (uint32_t k = 0; k + 1 < chunks; k += 2) {

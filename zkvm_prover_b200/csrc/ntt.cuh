@@ -281,6 +281,166 @@ __global__ void __launch_bounds__(THREADS, NTT_MIN_CTAS) pass_kernel(const PassP
 
 
 // ------------------------------------------------------------------------------------------------------------------
+// Direct pass (round 2): one CTA per tile, no staging copy.  The FIRST register round loads its rows straight from global
+// memory (LDG.128, eight lanes per 128-byte row segment) and the LAST one stores straight to global memory, so a tile crosses
+// shared memory twice per interior round boundary only: 4 tile-sized shared-memory transfers for K = 8 instead of the 8 of
+// the TMA ring (fill + 3 x (load, store) + drain).  Measured on B200 (profiles/ntt_lab_r02.txt): in the TMA kernel the
+// shared-memory time of a tile (2048 clk) ADDS to its arithmetic (2700 clk) instead of hiding under it, because all warps
+// of a CTA sit in the same phase; here 3-4 independent CTAs per SM are resident in different phases (global-load wait,
+// arithmetic, exchange), and the per-row factor tables are computed while the tile's loads are in flight.
+// K, LC are compile-time (index arithmetic folds away): tiles are 2^K rows x 2^LC columns = 2^13 elements, 256 threads,
+// 32 elements per thread as 8 rows x 4 adjacent columns.
+#ifndef NTT_DIRECT_CTAS
+#define NTT_DIRECT_CTAS 3
+#endif
+constexpr int DIRECT_THREADS = 256;
+
+template <int K, int LC, int k, int U, bool FROM_GLOBAL, bool TO_GLOBAL>
+__device__ __forceinline__ void direct_round(uint32_t* sm, const uint2* sm_tw, const PassParams& p, uint64_t row_base, uint32_t col0, int L, const uint2* fac_pre,
+                                             const uint2* fac_post, int tid) {
+    constexpr int LL = LC - 2, TILE_COLS = 1 << LC, R = 1 << k;
+    constexpr int lowbits = K - U - k;
+    constexpr int groups = 1 << (K - k + LL);
+    constexpr bool LAST = (U + k == K);
+    static_assert(groups % DIRECT_THREADS == 0 || groups < DIRECT_THREADS, "group count");
+#pragma unroll
+    for (int gi0 = 0; gi0 < groups; gi0 += DIRECT_THREADS) {
+        const int gi = gi0 + tid;
+        if (groups < DIRECT_THREADS && gi >= groups) break;
+        const int lane = gi & ((1 << LL) - 1);
+        const int g = gi >> LL;
+        const int highpart = g >> lowbits, lowpart = g & ((1 << lowbits) - 1);
+        const int base = (highpart << (K - U)) + lowpart;
+        const uint32_t col = col0 + lane * 4;
+        const bool col_ok = col < p.width;
+        Vec<4> x[R];
+        if (FROM_GLOBAL) {
+            const uint32_t* src = p.in + (row_base + ((uint64_t)base << L)) * p.in_pitch + col;
+            const uint64_t step = ((uint64_t)p.in_pitch << L) << lowbits;
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                if (col_ok) x[q].load(src + q * step);
+                else x[q].v[0] = x[q].v[1] = x[q].v[2] = x[q].v[3] = 0;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; q++) x[q].load(sm + (base + (q << lowbits)) * TILE_COLS + lane * 4);
+        }
+        if (fac_pre) {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const uint2 f = fac_pre[base + (q << lowbits)];
+#pragma unroll
+                for (int c = 0; c < 4; c++) x[q].v[c] = shoup_mul(x[q].v[c], f);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < k; v++) {
+            const int half = 1 << (k - 1 - v);
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                if (q & half) continue;
+                if (LAST && (q & (half - 1)) == 0) {  // w^0
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t a = x[q].v[c], b = x[q + half].v[c];
+                        x[q].v[c] = bb::add(a, b);
+                        x[q + half].v[c] = bb::sub(a, b);
+                    }
+                    continue;
+                }
+                const int e = (((q & (half - 1)) << lowbits) + lowpart) << (U + v);
+                const uint2 w = sm_tw[e];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t a = x[q].v[c], b = x[q + half].v[c];
+                    x[q].v[c] = bb::add(a, b);
+                    const uint32_t d = a - b + bb::P;
+                    const uint32_t qq = __umulhi(d, w.y);
+                    x[q + half].v[c] = bb::red2p(d * w.x - qq * bb::P);
+                }
+            }
+        }
+        if (fac_post) {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const uint2 f = fac_post[base + (q << lowbits)];
+#pragma unroll
+                for (int c = 0; c < 4; c++) x[q].v[c] = shoup_mul(x[q].v[c], f);
+            }
+        }
+        if (TO_GLOBAL) {
+            if (col_ok) {
+#pragma unroll
+                for (int q = 0; q < R; q++) {
+                    uint64_t row = row_base + ((uint64_t)(base + (q << lowbits)) << L);
+                    if (p.out_natural) row = bb::bitrev((uint32_t)row, p.n);
+                    x[q].store(p.out + row * p.out_pitch + col);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; q++) x[q].store(sm + (base + (q << lowbits)) * TILE_COLS + lane * 4);
+        }
+    }
+}
+
+template <int K, int LC>
+__global__ void __launch_bounds__(DIRECT_THREADS, NTT_DIRECT_CTAS) pass_kernel_direct(const PassParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int R = 1 << K, TILE_COLS = 1 << LC;
+    uint32_t* sm = smem;                                                     // [R][TILE_COLS]
+    uint2* sm_tw = reinterpret_cast<uint2*>(smem + R * TILE_COLS);           // [R/2] local roots (Shoup pairs)
+    uint2* sm_fac = sm_tw + R / 2;                                           // [2][R] prescale, twist (Shoup pairs)
+    const int tid = threadIdx.x;
+    const int n = p.n, s0 = p.s0;
+    const int L = n - s0 - K;
+    const uint32_t col_tiles = (p.width + TILE_COLS - 1) >> LC;
+    const uint32_t ct = blockIdx.x % col_tiles;
+    const uint64_t rt = blockIdx.x / col_tiles;
+    const uint64_t low = rt & ((1ull << L) - 1);
+    const uint64_t high = rt >> L;
+    const uint64_t row_base = (high << (n - s0)) + low;
+    const uint32_t col0 = ct << LC;
+    const bool need_twist = L > 0 && low != 0;
+    const uint2* fac_pre = p.pre_lo ? sm_fac : nullptr;
+    const uint2* fac_post = need_twist ? sm_fac + R : nullptr;
+
+    // tables first (their L2 look-ups overlap the first round's global loads, which do not depend on them until the
+    // barrier below); R <= 256 rows, one per thread
+    for (int i = tid; i < R / 2; i += DIRECT_THREADS) sm_tw[i] = __ldg(p.tw_local + i);
+    for (int t = tid; t < R; t += DIRECT_THREADS) {
+        if (p.pre_lo) sm_fac[t] = shoup_pair(pow2level(p.pre_lo, p.pre_hi, row_base + ((uint64_t)t << L)));
+        if (need_twist) {
+            uint64_t e = (low * (uint64_t)bb::bitrev((uint32_t)t, K)) << s0;
+            if (p.inverse) e = ((1ull << n) - e) & ((1ull << n) - 1);
+            sm_fac[R + t] = shoup_pair(pow2level(p.tw_lo, p.tw_hi, e));
+        }
+    }
+    __syncthreads();
+    constexpr int REM = K % 3;
+    if (K <= 3) {
+        direct_round<K, LC, K, 0, true, true>(sm, sm_tw, p, row_base, col0, L, fac_pre, fac_post, tid);
+    } else if (REM == 0) {
+        direct_round<K, LC, 3, 0, true, false>(sm, sm_tw, p, row_base, col0, L, fac_pre, nullptr, tid);
+        __syncthreads();
+        if (K == 9) {
+            direct_round<K, LC, 3, 3, false, false>(sm, sm_tw, p, row_base, col0, L, nullptr, nullptr, tid);
+            __syncthreads();
+        }
+        direct_round<K, LC, 3, K - 3, false, true>(sm, sm_tw, p, row_base, col0, L, nullptr, fac_post, tid);
+    } else {
+        direct_round<K, LC, REM, 0, true, false>(sm, sm_tw, p, row_base, col0, L, fac_pre, nullptr, tid);
+        __syncthreads();
+        if (K > 6) {
+            direct_round<K, LC, 3, REM, false, false>(sm, sm_tw, p, row_base, col0, L, nullptr, nullptr, tid);
+            __syncthreads();
+        }
+        direct_round<K, LC, 3, K - 3, false, true>(sm, sm_tw, p, row_base, col0, L, nullptr, fac_post, tid);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // TMA pass: the same K stages, as a persistent warp-specialised kernel.  One producer warp moves whole tiles between
 // HBM and shared memory with cp.async.bulk.tensor (one 4-D box per tile: {columns, low, t, high} of the strided row set)
 // through a 3-stage mbarrier ring; 256 consumer threads only ever touch shared memory, so butterflies of tile c overlap

@@ -23,6 +23,8 @@ from typing import List, Optional
 
 import numpy as np
 
+from .field import P as P_MOD, from_monty, monty_scalar
+
 DIGEST = 8
 EF_D = 4
 
@@ -159,7 +161,7 @@ class FriProof:
     commit_phase_commits: np.ndarray          # (rounds, 8)
     query_proofs: List[QueryProof]
     final_poly: np.ndarray                    # (final_poly_len, 4)
-    pow_witness: int
+    pow_witness: int                          # CANONICAL witness (what grind returns and check_witness takes); the wire word is its Montgomery form
 
     def write(self, w: _Writer):
         w.u64(len(self.commit_phase_commits))
@@ -167,7 +169,9 @@ class FriProof:
         w.vec(self.query_proofs, lambda q: q.write(w))
         w.u64(len(self.final_poly))
         w.words(self.final_poly)
-        w.u32(self.pow_witness)
+        # `pow_witness: Val` is a field element like every other one on the wire: serde writes MontyField31's inner u32,
+        # i.e. the Montgomery representation.  Writing the canonical integer makes a p3 verifier observe a different element.
+        w.u32(monty_scalar(self.pow_witness))
 
     @staticmethod
     def read(r: _Reader) -> "FriProof":
@@ -176,7 +180,7 @@ class FriProof:
         queries = r.vec(lambda: QueryProof.read(r), 16)
         m = r._len(16)
         final_poly = r.words(m * EF_D).reshape(m, EF_D)
-        return FriProof(commits, queries, final_poly, r.u32())
+        return FriProof(commits, queries, final_poly, int(from_monty(np.uint32(r.u32()))))
 
     def encode(self) -> bytes:
         w = _Writer()
@@ -286,7 +290,7 @@ class Proof:
     fri: FriProof
     opened: OpenedValues
     per_air: List[AirProofData]
-    logup_pow_witness: Optional[int] = None
+    logup_pow_witness: Optional[int] = None    # canonical, like FriProof.pow_witness (Montgomery word on the wire)
 
     def write(self, w: _Writer):
         for c in (self.main_trace_commits, self.after_challenge_commits):
@@ -300,7 +304,7 @@ class Proof:
             w.u8(0)
         else:
             w.u8(1)
-            w.u32(self.logup_pow_witness)
+            w.u32(monty_scalar(self.logup_pow_witness))
 
     @staticmethod
     def read(r: _Reader) -> "Proof":
@@ -315,7 +319,7 @@ class Proof:
         tag = r.u8()
         if tag not in (0, 1):
             raise ValueError("bad Option tag")
-        return Proof(commits[0], commits[1], quotient, fri, opened, per_air, r.u32() if tag else None)
+        return Proof(commits[0], commits[1], quotient, fri, opened, per_air, int(from_monty(np.uint32(r.u32()))) if tag else None)
 
 
 @dataclass
