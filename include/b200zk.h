@@ -114,8 +114,6 @@ int b200zk_merkle_commit(b200zk_ctx*, b200zk_mat* const* mats, uint32_t k, int t
  * inside the tree, commit them; the extended matrices never leave the device. */
 int b200zk_lde_commit(b200zk_ctx*, b200zk_mat* const* evals, uint32_t k, uint32_t added_bits,
                       const uint32_t* shifts_monty, uint32_t h_root[8], b200zk_tree** out);
-int b200zk_lde_commit_fused(b200zk_ctx*, b200zk_mat* const* evals, uint32_t k, uint32_t added_bits,
-                            const uint32_t* shifts_monty, uint32_t h_root[8], b200zk_tree** out); /* alias of b200zk_lde_commit */
 /* the same for ONE trace that still lives in host memory (pinned for full speed): the matrix is processed in column
  * strips so the host->device transfer of strip s+1 overlaps the LDE and leaf hashing of strip s (copy stream + compute
  * stream).  strip_cols = 0 picks the strip width; small or ragged inputs take the plain upload path.  Bit-identical to

@@ -1205,12 +1205,6 @@ int b200zk_lde_commit(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uin
 }
 
 
-// the name SURVEY.md section 8(b-iii) proposes for the same entry point
-int b200zk_lde_commit_fused(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uint32_t added_bits, const uint32_t* shifts, uint32_t h_root[8],
-                            b200zk_tree** out) {
-    return b200zk_lde_commit(ctx, evals, k, added_bits, shifts, h_root, out);
-}
-
 // ---- TwoAdicFriPcs::commit of ONE host-resident trace with the transfer hidden behind the arithmetic -------------------
 // Everything before tree building is column-local (NTT) or column-sequential (sponge), so the trace is processed in
 // column strips: strip s+1 crosses PCIe on the copy stream while strip s is extended and absorbed on the compute stream.
