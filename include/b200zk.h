@@ -155,6 +155,9 @@ int b200zk_chal_sample_bits(b200zk_ctx*, b200zk_chal*, uint32_t bits, uint32_t* 
  * bits == 0 follows p3-challenger 0.4.3 (the reference's pin, Cargo.lock:5576): witness 0, transcript untouched. */
 int b200zk_chal_grind(b200zk_ctx*, b200zk_chal*, uint32_t bits, uint32_t* h_witness);
 int b200zk_chal_state(b200zk_ctx*, const b200zk_chal*, uint32_t h_state[16 + 8 + 1 + 8 + 1]);
+/* the inverse: load the fields of a host DuplexChallenger (same 34-word layout; fill counts <= 8, elements reduced), so a
+ * transcript driven on the host can hand over to the device for the FRI commit phase and take the state back afterwards */
+int b200zk_chal_set_state(b200zk_ctx*, b200zk_chal*, const uint32_t h_state[16 + 8 + 1 + 8 + 1]);
 
 /* ---- K6: FRI commit phase.  Replaces p3_fri::prover::commit_phase + TwoAdicFriGenericConfig::fold_matrix */
 /* one round, host challenger in between (two calls):

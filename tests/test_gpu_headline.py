@@ -152,3 +152,22 @@ def test_grind_zero_bits_leaves_transcript_alone(z, ctx):
     assert c.grind(0) == 0 and o.grind(0) == 0
     assert np.array_equal(c.state(), before) and np.array_equal(c.state(), o.state())
     assert c.grind(6) == o.grind(6) and np.array_equal(c.state(), o.state())
+
+
+def test_challenger_state_handover(z, ctx):
+    """b200zk_chal_set_state: a transcript can move between a host challenger and the device one at any point"""
+    a, o = z.DuplexChallenger(ctx), O.Challenger()
+    v = np.arange(3, 16, dtype=np.uint32)
+    a.observe(v)
+    o.observe(v)
+    assert a.sample() == o.sample()
+    b = z.DuplexChallenger(ctx).set_state(o.state())          # hand the ORACLE's (host) state to a fresh device challenger
+    for _ in range(11):
+        assert b.sample() == a.sample()
+    b.observe(v[:5])
+    a.observe(v[:5])
+    assert np.array_equal(a.state(), b.state())
+    bad = a.state().copy()
+    bad[24] = 9
+    with pytest.raises(z.B200zkError):
+        b.set_state(bad)

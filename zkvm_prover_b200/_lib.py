@@ -87,6 +87,7 @@ _SIGS = {
     "b200zk_chal_sample_bits": (_int, [_p, _p, _u32, _p]),
     "b200zk_chal_grind": (_int, [_p, _p, _u32, _p]),
     "b200zk_chal_state": (_int, [_p, _p, _p]),
+    "b200zk_chal_set_state": (_int, [_p, _p, _p]),
     "b200zk_fri_commit_layer": (_int, [_p, _p, _u64, _p, C.POINTER(_p)]),
     "b200zk_fri_fold_layer": (_int, [_p, _p, _u64, _p, _p, _p]),
     "b200zk_fri_commit_phase": (_int, [_p, C.POINTER(_p), C.POINTER(_u64), _u32, _u32, _u32, _p, _p, _p, _p, _p, C.POINTER(_p), C.POINTER(_u32)]),

@@ -56,6 +56,12 @@ class DuplexChallenger:
         self.ctx.check(self.ctx.lib.b200zk_chal_state(self.ctx.h, self.h, out.ctypes.data))
         return out
 
+    def set_state(self, state):
+        """load the 34 words `state()` returns (e.g. a host DuplexChallenger's sponge state | input buffer | fill | output buffer | fill)"""
+        s = np.ascontiguousarray(state, dtype=np.uint32).reshape(34)
+        self.ctx.check(self.ctx.lib.b200zk_chal_set_state(self.ctx.h, self.h, s.ctypes.data))
+        return self
+
     def free(self):
         if self.h and self.ctx.h:
             self.ctx.lib.b200zk_chal_free(self.ctx.h, self.h)

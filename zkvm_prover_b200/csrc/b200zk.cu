@@ -1558,6 +1558,19 @@ int b200zk_chal_state(b200zk_ctx* ctx, const b200zk_chal* c, uint32_t h_state[34
     return B200ZK_OK;
 }
 
+// the inverse of b200zk_chal_state: load a host DuplexChallenger's fields, so a transcript driven on the host can hand over to
+// the device for the FRI commit phase and take the advanced state back afterwards (bindings/b200zk-p3/src/challenger.rs)
+int b200zk_chal_set_state(b200zk_ctx* ctx, b200zk_chal* c, const uint32_t h_state[34]) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    if (!c || !h_state) return fail(ctx, B200ZK_ERR_ARG, "null challenger/state");
+    if (h_state[24] > 8 || h_state[33] > 8) return fail(ctx, B200ZK_ERR_ARG, "buffer fill counts must be <= 8");
+    for (int i = 0; i < 34; i++)
+        if (i != 24 && i != 33 && h_state[i] >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "state word is not a reduced field element");
+    CU(cudaMemcpyAsync(c->d, h_state, sizeof(fri::ChalState), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // h_state may be a temporary
+    return B200ZK_OK;
+}
+
 // ================================================================================================ FRI
 static int fold_launch(b200zk_ctx* ctx, const uint32_t* d_in, uint64_t len, const uint32_t* d_beta, const uint32_t* d_add, int add_mode, uint32_t* tab,
                        uint32_t* d_out) {
