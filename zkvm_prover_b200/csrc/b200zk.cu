@@ -38,6 +38,8 @@ struct b200zk_ctx {
     uint32_t* tw_hi[MAX_LOG + 1] = {};
     uint32_t* tab = nullptr;  // scratch for per-call power tables (stream ordered reuse)
     size_t tab_words = 0;
+    uint2* mid_sigma = nullptr;  // [cosets][2^K] coset powers of the fused LDE middle (stream ordered reuse)
+    size_t mid_sigma_pairs = 0;
     uint32_t* d_small = nullptr;  // 64 KB of small device scratch (roots, betas, flags)
     int max_smem_optin = 0;
     int num_sms = 148;
@@ -323,8 +325,12 @@ struct Scatter {
     uint64_t g0 = 0, mg = 0, slot_off = 0;
 };
 
+// A caller may hand in its own pass plan and run only the passes [pass_begin, pass_end) of it (the fused LDE middle,
+// lde_core below, replaces the last inverse pass and the first forward pass): the first pass that runs reads `src`, the
+// coset prescale belongs to pass 0 and the `last` duties (dst_final, post scale, natural order, scatter) to the plan's final pass.
 int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t* dst_final, int n, uint32_t width, int inverse, Scale pre,
-                  Scale post, int out_natural, uint32_t src_pitch = 0, uint32_t work_pitch = 0, uint32_t dst_pitch = 0, const Scatter* scatter = nullptr) {
+                  Scale post, int out_natural, uint32_t src_pitch = 0, uint32_t work_pitch = 0, uint32_t dst_pitch = 0, const Scatter* scatter = nullptr,
+                  const std::vector<int>* plan_in = nullptr, size_t pass_begin = 0, size_t pass_end = ~(size_t)0) {
     if (!src_pitch) src_pitch = width;
     if (!work_pitch) work_pitch = width;
     if (!dst_pitch) dst_pitch = width;
@@ -334,11 +340,13 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
                         ? 4
                         : 1;
     const bool tma_ok = vec == 4 && ctx->encode_tiled && tma_enabled();
-    std::vector<int> plan = make_plan(n, tma_ok ? ntt::TMA_MAX_K : 0);
+    std::vector<int> plan = plan_in ? *plan_in : make_plan(n, tma_ok ? ntt::TMA_MAX_K : 0);
+    pass_end = std::min(pass_end, plan.size());
     int s0 = 0;
-    for (size_t i = 0; i < plan.size(); i++) {
+    for (size_t i = 0; i < pass_begin && i < plan.size(); i++) s0 += plan[i];
+    for (size_t i = pass_begin; i < pass_end; i++) {
         const int K = plan[i];
-        const bool first = i == 0, last = i + 1 == plan.size();
+        const bool first = i == pass_begin, last = i + 1 == plan.size();
         TRY(ensure_local(ctx, inverse, K));
         ntt::PassParams p;
         p.in = first ? src : work;
@@ -360,8 +368,8 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         p.tw_local = ctx->tw_local[inverse][K];
         p.tw_lo = ctx->tw_lo[n];
         p.tw_hi = ctx->tw_hi[n];
-        p.pre_lo = first ? pre.lo : nullptr;
-        p.pre_hi = first ? pre.hi : nullptr;
+        p.pre_lo = i == 0 ? pre.lo : nullptr;
+        p.pre_hi = i == 0 ? pre.hi : nullptr;
         p.post_lo = last ? post.lo : nullptr;
         p.post_hi = last ? post.hi : nullptr;
         p.out_natural = last ? out_natural : 0;
@@ -500,10 +508,12 @@ const char* b200zk_version(void) { return "b200zk 0.1 (sm_100a)"; }
 static int configure_kernels(int max_smem_optin) {
     const void* big[] = {(const void*)ntt::pass_kernel_tma, (const void*)ntt::pass_kernel<4>, (const void*)ntt::pass_kernel<1>,
                          (const void*)ntt::pass_kernel_direct<8, 5>, (const void*)ntt::pass_kernel_direct<7, 6>, (const void*)ntt::pass_kernel_direct<6, 7>,
+                         (const void*)ntt::lde_mid_kernel<8, 5, 256, 3>, (const void*)ntt::lde_mid_kernel<7, 6, 256, 3>, (const void*)ntt::lde_mid_kernel<6, 7, 256, 3>,
+                         (const void*)ntt::lde_mid_kernel<7, 5, 128, 6>, (const void*)ntt::lde_mid_kernel<6, 6, 128, 6>,
                          (const void*)op::dot_ext_powers_kernel<4>, (const void*)op::dot_ext_powers_kernel<1>};
     for (const void* f : big)
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return B200ZK_ERR_CUDA;
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 11; i++)
         if (cudaFuncSetAttribute(big[i], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) return B200ZK_ERR_CUDA;
     return B200ZK_OK;
 }
@@ -576,6 +586,7 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     for (auto& p : ctx->tw_lo) cudaFree(p);
     for (auto& p : ctx->tw_hi) cudaFree(p);
     cudaFree(ctx->tab);
+    cudaFree(ctx->mid_sigma);
     cudaFree(ctx->d_small);
     if (ctx->copy_stream) {
         cudaStreamDestroy(ctx->copy_stream);
@@ -698,6 +709,27 @@ int b200zk_mat_checksum(b200zk_ctx* ctx, const b200zk_mat* m, uint64_t* h_out) {
 
 
 namespace {
+bool mid_enabled() {
+    static const int v = [] {
+        const char* e = getenv("B200ZK_LDE_FUSED_MID");  // experiment knob: 0 keeps the unfused pass sequence
+        return e ? atoi(e) : 1;
+    }();
+    return v != 0;
+}
+
+// pass plan of a fused LDE: the inverse runs `rest` then the K_mid stages, every forward transform K_mid then `rest`
+int mid_plan(int n, std::vector<int>* rest) {
+    const int m = (n + ntt::TMA_MAX_K - 1) / ntt::TMA_MAX_K;
+    int km = std::max(6, std::min(8, n - ntt::TMA_MAX_K * (m - 1)));
+    static const int km_force = [] {
+        const char* e = getenv("B200ZK_MID_K");  // experiment knob: force the stage count of the fused middle (6..8)
+        return e ? atoi(e) : 0;
+    }();
+    if (km_force >= 6 && km_force <= 8 && km_force <= n) km = km_force;
+    *rest = make_plan(n - km, ntt::TMA_MAX_K);
+    return km;
+}
+
 // per-coset scale tables of an LDE: (shift * w'^bitrev(c))^j / N for every coset block c, in ctx->tab
 int lde_tables(b200zk_ctx* ctx, int n, uint32_t added_bits, uint32_t shift) {
     const uint64_t N = 1ull << n;
@@ -710,18 +742,120 @@ int lde_tables(b200zk_ctx* ctx, int n, uint32_t added_bits, uint32_t shift) {
         uint32_t base = bb::mul(shift, bb::pow(wprime, bb::bitrev(c, (int)added_bits)));
         TRY(pow_tables(ctx, ctx->tab + per * c, ctx->tab + per * c + lo_words(N), base, ninv, N));
     }
+    if (n >= 6 && C <= (uint32_t)ntt::MID_MAX_COSETS) {  // coset powers of the fused middle: sigma_c[k] = (base_c^(2^(n-K)))^k
+        std::vector<int> rest;
+        const int km = mid_plan(n, &rest);
+        const uint32_t R = 1u << km;
+        if (ctx->mid_sigma_pairs < (size_t)C * R) {
+            if (ctx->mid_sigma) dev_free(ctx, ctx->mid_sigma);
+            ctx->mid_sigma = nullptr;
+            ctx->mid_sigma_pairs = 0;
+            TRY(dev_alloc(ctx, (size_t)C * R * 8, (void**)&ctx->mid_sigma));
+            ctx->mid_sigma_pairs = (size_t)C * R;
+        }
+        for (uint32_t c = 0; c < C; c++) {
+            uint32_t base = bb::mul(shift, bb::pow(wprime, bb::bitrev(c, (int)added_bits)));
+            for (int i = 0; i < n - km; i++) base = bb::mul(base, base);
+            ntt::mid_sigma_kernel<<<(R + 255) / 256, 256, 0, ctx->stream>>>(ctx->mid_sigma + (size_t)c * R, base, R);
+            LAUNCHED();
+        }
+    }
     return B200ZK_OK;
 }
 
 // coset LDE of `width` columns (n >= 1, bit-reversed rows out); src / dst may be column strips of wider matrices
 // (pitches in elements).  Needs lde_tables() for the same (n, added_bits, shift) to have been enqueued.
-// Work space is the destination itself: block 0 holds the inverse transform in flight, the natural-order coefficients
-// land in the last block, and every coset block is produced from them (the last one in place).
+//
+// Fused form (vectorisable shapes, n >= 6): inverse passes but the last -> `scratch` (N x width; may alias src when the
+// caller owns src, else a temporary); ntt::lde_mid_kernel finishes the inverse, applies the coset powers and runs the first
+// forward pass of every coset straight into the coset blocks; the remaining forward passes run in place per block.
+// Unfused form: work space is the destination itself: block 0 holds the inverse transform in flight, the natural-order
+// coefficients land in the last block, and every coset block is produced from them (the last one in place).
 int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, uint32_t width, uint32_t added_bits, uint32_t* dst, uint32_t dst_pitch,
-             const Scatter* scatter = nullptr) {
+             const Scatter* scatter = nullptr, uint32_t* scratch = nullptr, uint32_t scratch_pitch = 0) {
     const uint64_t N = 1ull << n;
     const uint32_t C = 1u << added_bits;
     const size_t per = lo_words(N) + hi_words(N);
+    const bool vec4 = width % 4 == 0 && src_pitch % 4 == 0 && dst_pitch % 4 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0 &&
+                      (!scratch || ((uintptr_t)scratch % 16 == 0 && scratch_pitch % 4 == 0));
+    std::vector<int> rest;
+    const int km = n >= 6 ? mid_plan(n, &rest) : 0;
+    if (mid_enabled() && vec4 && ctx->encode_tiled && tma_enabled() && n >= 6 && C <= (uint32_t)ntt::MID_MAX_COSETS && !(scatter && rest.empty()) &&
+        (N >> km) * ((width + (1u << (13 - km)) - 1) >> (13 - km)) <= 0x7fffffffull) {
+        const uint64_t R = 1ull << km;
+        const int lcm = 13 - km;
+        std::vector<int> inv_plan = rest, fwd_plan = {km};
+        inv_plan.push_back(km);
+        fwd_plan.insert(fwd_plan.end(), rest.begin(), rest.end());
+        TRY(ensure_roots(ctx, n));
+        TRY(ensure_local(ctx, 0, km));
+        TRY(ensure_local(ctx, 1, km));
+        if (ctx->mid_sigma_pairs < C * R) return fail(ctx, B200ZK_ERR_ARG, "internal: lde_tables was not run for this shape");
+        ntt::MidParams mp{};
+        uint32_t* tmp = nullptr;
+        const uint32_t* mid_in = src;
+        uint32_t mid_pitch = src_pitch;
+        int rc = B200ZK_OK;
+        if (!rest.empty()) {
+            uint32_t* work = scratch;
+            uint32_t wpitch = scratch_pitch ? scratch_pitch : width;
+            if (!work) {
+                rc = dev_alloc(ctx, N * width * 4, (void**)&tmp);
+                work = tmp;
+                wpitch = width;
+            }
+            if (rc == B200ZK_OK)
+                rc = run_transform(ctx, src, work, work, n, width, /*inverse=*/1, Scale{}, Scale{}, 0, src_pitch, wpitch, wpitch, nullptr, &inv_plan, 0, inv_plan.size() - 1);
+            mid_in = work;
+            mid_pitch = wpitch;
+        }
+        if (rc == B200ZK_OK) {
+            mp.in = mid_in;
+            mp.out = dst;
+            mp.block_stride = N * dst_pitch;
+            mp.in_pitch = mid_pitch;
+            mp.out_pitch = dst_pitch;
+            mp.width = width;
+            mp.n = n;
+            mp.cosets = (int)C;
+            mp.tw_inv = ctx->tw_local[1][km];
+            mp.tw_fwd = ctx->tw_local[0][km];
+            mp.tw_lo = ctx->tw_lo[n];
+            mp.tw_hi = ctx->tw_hi[n];
+            mp.sigma = ctx->mid_sigma;
+            for (uint32_t c = 0; c < C; c++) {
+                mp.pre_lo[c] = ctx->tab + per * c;
+                mp.pre_hi[c] = ctx->tab + per * c + lo_words(N);
+            }
+            static const int small_tile = [] {
+                const char* e = getenv("B200ZK_MID_TILE");  // experiment knob: 12 = 2^12-element tiles, 128 threads, six CTAs per SM (K = 6, 7)
+                return e ? atoi(e) == 12 : 1;   // measured: 10.06 vs 10.99 ms at 2^23 x 256 (barrier stalls span 4 warps instead of 8)
+            }();
+            const bool small = small_tile && km <= 7;
+            const int lct = small ? 12 - km : lcm;
+            const uint64_t tiles = (N >> km) * ((width + (1u << lct) - 1) >> lct);
+            const size_t dsm = 2 * ((size_t)R << lct) * 4 + R * 8 + (size_t)C * R * 8;
+            PassTimer tm(ctx, "mid", n, n - km, km, width);
+            if (small && km == 7) ntt::lde_mid_kernel<7, 5, 128, 6><<<(uint32_t)tiles, 128, dsm, ctx->stream>>>(mp);
+            else if (small) ntt::lde_mid_kernel<6, 6, 128, 6><<<(uint32_t)tiles, 128, dsm, ctx->stream>>>(mp);
+            else if (km == 8) ntt::lde_mid_kernel<8, 5, 256, 3><<<(uint32_t)tiles, 256, dsm, ctx->stream>>>(mp);
+            else if (km == 7) ntt::lde_mid_kernel<7, 6, 256, 3><<<(uint32_t)tiles, 256, dsm, ctx->stream>>>(mp);
+            else ntt::lde_mid_kernel<6, 7, 256, 3><<<(uint32_t)tiles, 256, dsm, ctx->stream>>>(mp);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B200ZK_ERR_CUDA, "lde_mid launch failed");
+        }
+        for (uint32_t c = 0; c < C && rc == B200ZK_OK && !rest.empty(); c++) {
+            uint32_t* blk = dst + (uint64_t)c * N * dst_pitch;
+            Scatter sc;
+            if (scatter) {
+                sc = *scatter;
+                sc.g0 = (uint64_t)c * N;
+            }
+            rc = run_transform(ctx, blk, blk, blk, n, width, /*inverse=*/0, Scale{}, Scale{}, 0, dst_pitch, dst_pitch, dst_pitch, scatter ? &sc : nullptr, &fwd_plan, 1);
+        }
+        if (tmp) dev_free(ctx, tmp);
+        return rc;
+    }
     uint32_t* coef = dst + (uint64_t)(C - 1) * N * dst_pitch;
     b200zk_mat* tmp_inv = nullptr;
     uint32_t* inv_work = dst;  // block 0
@@ -785,7 +919,7 @@ int b200zk_coset_lde_batch_into(b200zk_ctx* ctx, const b200zk_mat* evals, uint32
         if (rc == B200ZK_OK) {
             repitch_kernel<<<(uint32_t)((N * Wp + 255) / 256), 256, 0, ctx->stream>>>(evals->d, W, W, pin, Wp, Wp, N);
             ctx->launches++;
-            rc = lde_core(ctx, pin, Wp, n, Wp, added_bits, pout, Wp);
+            rc = lde_core(ctx, pin, Wp, n, Wp, added_bits, pout, Wp, nullptr, /*scratch=*/pin, Wp);
         }
         if (rc == B200ZK_OK) {
             repitch_kernel<<<(uint32_t)((M * W + 255) / 256), 256, 0, ctx->stream>>>(pout, Wp, W, final_dst, W, W, M);
@@ -1182,7 +1316,7 @@ int b200zk_lde_commit(b200zk_ctx* ctx, b200zk_mat* const* evals, uint32_t k, uin
             ctx->launches++;
             off += m->width;
         }
-        if (rc == B200ZK_OK) rc = lde_core(ctx, pin, (uint32_t)wp, n, (uint32_t)wp, added_bits, pout, (uint32_t)wp);
+        if (rc == B200ZK_OK) rc = lde_core(ctx, pin, (uint32_t)wp, n, (uint32_t)wp, added_bits, pout, (uint32_t)wp, nullptr, /*scratch=*/pin, (uint32_t)wp);
         off = 0;
         for (size_t g = 0; g < grp.size() && rc == B200ZK_OK; g++) {
             const uint32_t j = grp[g];
@@ -1250,7 +1384,7 @@ int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
         copies_in_flight = true;
         if (!cuda_ok(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream), "event record")) break;
         if (!cuda_ok(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0), "stream wait")) break;
-        rc = lde_core(ctx, sbuf[b], j.strip, n, j.strip, j.added_bits, j.lde->d + (size_t)s * j.strip, j.W);
+        rc = lde_core(ctx, sbuf[b], j.strip, n, j.strip, j.added_bits, j.lde->d + (size_t)s * j.strip, j.W, nullptr, /*scratch=*/sbuf[b], j.strip);
         if (rc != B200ZK_OK) break;
         if (!cuda_ok(cudaEventRecord(ctx->ev_consumed[b], ctx->stream), "event record")) break;
         mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, ctx->stream>>>(j.lde->d, j.W, s * j.strip, j.strip, M, cap, s == 0, s + 1 == strips,

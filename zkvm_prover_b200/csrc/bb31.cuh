@@ -42,8 +42,19 @@ static __device__ __constant__ uint32_t K_27 = 27u, K_31 = 31u;
 #endif
 #ifdef __CUDA_ARCH__
 BB_HD uint32_t fadd(uint32_t a, uint32_t b) { return a * K_ONE + b; }
+#ifndef BB_AADD_MODE
+#define BB_AADD_MODE 0  // how an addition is pinned to the ALU pipe: 0 = three-input IADD3 with an opaque zero, 1 = add.cc (carry-out form), 2 = not pinned
+#endif
+#if BB_AADD_MODE == 0
 BB_HD uint32_t aadd(uint32_t a, uint32_t b) { return a + b + K_ZERO; }
 BB_HD uint32_t asub(uint32_t a, uint32_t b) { return a - b + K_ZERO; }
+#elif BB_AADD_MODE == 1
+BB_HD uint32_t aadd(uint32_t a, uint32_t b) { uint32_t r; asm("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BB_HD uint32_t asub(uint32_t a, uint32_t b) { uint32_t r; asm("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#else
+BB_HD uint32_t aadd(uint32_t a, uint32_t b) { return a + b; }
+BB_HD uint32_t asub(uint32_t a, uint32_t b) { return a - b; }
+#endif
 BB_HD uint64_t fadd64(uint64_t acc, uint32_t x) { return (uint64_t)x * K_ONE + acc; }
 BB_HD int32_t mulhi32(int32_t a, int32_t b) { return __mulhi(a, b); }
 #else

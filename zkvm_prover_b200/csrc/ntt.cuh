@@ -441,6 +441,189 @@ __global__ void __launch_bounds__(DIRECT_THREADS, NTT_DIRECT_CTAS) pass_kernel_d
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Fused middle of a coset LDE (round 2).  The tile the LAST inverse pass finishes -- positions [j 2^K, (j+1) 2^K), which hold
+// the coefficients  k 2^(n-K) + q,  k = bitrev_K(slot), q = bitrev_(n-K)(j)  -- is exactly the tile the FIRST forward pass of
+// every coset starts from.  One CTA therefore: loads the tile once, finishes the inverse transform in shared memory, and for
+// each coset c multiplies by the coset powers and runs the first K forward stages, storing straight into coset block c.
+// The matrix is read once and written C times instead of being read 1 + C times and written 1 + C times (for log_blowup 1:
+// 3 sweeps of 8 B/element instead of 6), and the natural-order coefficient matrix never exists in HBM.
+//   prescale  s_c^(k 2^(n-K) + q) / N  =  sigma_c[k] * (s_c^q / N):  sigma is tile independent (a 2^K-entry table per coset),
+//   the per-tile scalar is folded into the twist  w_N^(q * bitrev_K(slot))  that the first forward pass applies anyway.
+// The forward rounds read the inverse result through bit-reversed slot numbers (whole 2^LC-column rows move, so any row
+// permutation is bank-conflict free) -- no reordering pass.  Tiles are 2^13 elements; shared memory holds the inverse
+// result X, a work tile Y, both local root tables and the twists: 70 KB, three CTAs per SM.
+constexpr int MID_MAX_COSETS = 8;
+#ifndef NTT_MID_CTAS
+#define NTT_MID_CTAS 3
+#endif
+struct MidParams {
+    const uint32_t* in;       // inverse transform after all but its last pass (2^n rows, DIF positions)
+    uint32_t* out;            // coset block c = out + c * block_stride
+    uint64_t block_stride;    // elements between coset blocks
+    uint32_t in_pitch, out_pitch, width;
+    int n, cosets;
+    const uint2* tw_inv;      // 2^(K-1) local inverse roots (Shoup pairs)
+    const uint2* tw_fwd;      // 2^(K-1) local forward roots
+    const uint32_t* tw_lo;    // w_N^i, two-level
+    const uint32_t* tw_hi;
+    const uint2* sigma;       // [cosets][2^K]: s_c^(k 2^(n-K)) as Shoup pairs
+    const uint32_t* pre_lo[MID_MAX_COSETS];  // two-level tables of s_c^j / N (the ones the unfused prescale uses)
+    const uint32_t* pre_hi[MID_MAX_COSETS];
+};
+enum MidSrc { MID_FROM_GLOBAL = 0, MID_FROM_SMEM = 1, MID_FROM_SMEM_BREV = 2 };
+
+// one register round (k stages starting at local stage U) of a 2^K-point DIF over a 2^K x 2^LC tile, 256 threads, a thread
+// owning 2^k rows x 4 adjacent columns (NT threads per CTA, 32 elements per thread and round).  g_in / g_out already point at this thread's column; *_step = elements per slot.
+template <int K, int LC, int NT, int k, int U, int SRC, bool TO_GLOBAL>
+__device__ __forceinline__ void mid_round(const uint32_t* sm_in, uint32_t* sm_out, const uint2* sm_tw, const uint32_t* g_in, uint64_t g_in_step, uint32_t* g_out,
+                                          uint64_t g_out_step, bool col_ok, const uint2* fac_pre, const uint2* fac_post, int tid) {
+    constexpr int LL = LC - 2, TILE_COLS = 1 << LC, R = 1 << k;
+    constexpr int lowbits = K - U - k;
+    constexpr int groups = 1 << (K - k + LL);
+    constexpr bool LAST = (U + k == K);
+    static_assert(groups % NT == 0, "group count");
+#pragma unroll
+    for (int gi0 = 0; gi0 < groups; gi0 += NT) {
+        const int gi = gi0 + tid;
+        const int lane = gi & ((1 << LL) - 1);
+        const int g = gi >> LL;
+        const int highpart = g >> lowbits, lowpart = g & ((1 << lowbits) - 1);
+        const int base = (highpart << (K - U)) + lowpart;
+        Vec<4> x[R];
+        if (SRC == MID_FROM_GLOBAL) {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                if (col_ok) x[q].load(g_in + (uint64_t)(base + (q << lowbits)) * g_in_step);
+                else x[q].v[0] = x[q].v[1] = x[q].v[2] = x[q].v[3] = 0;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const int slot = base + (q << lowbits);
+                const int src = SRC == MID_FROM_SMEM_BREV ? (int)(__brev((uint32_t)slot) >> (32 - K)) : slot;
+                x[q].load(sm_in + src * TILE_COLS + lane * 4);
+            }
+        }
+        if (fac_pre) {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const uint2 f = __ldg(fac_pre + base + (q << lowbits));
+#pragma unroll
+                for (int c = 0; c < 4; c++) x[q].v[c] = shoup_mul(x[q].v[c], f);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < k; v++) {
+            const int half = 1 << (k - 1 - v);
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                if (q & half) continue;
+                if (LAST && (q & (half - 1)) == 0) {  // w^0
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t a = x[q].v[c], b = x[q + half].v[c];
+                        x[q].v[c] = bb::add(a, b);
+                        x[q + half].v[c] = bb::sub(a, b);
+                    }
+                    continue;
+                }
+                const int e = (((q & (half - 1)) << lowbits) + lowpart) << (U + v);
+                const uint2 w = sm_tw[e];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t a = x[q].v[c], b = x[q + half].v[c];
+                    x[q].v[c] = bb::add(a, b);
+                    const uint32_t d = a - b + bb::P;
+                    const uint32_t qq = __umulhi(d, w.y);
+                    x[q + half].v[c] = bb::red2p(d * w.x - qq * bb::P);
+                }
+            }
+        }
+        if (fac_post) {
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                const uint2 f = fac_post[base + (q << lowbits)];
+#pragma unroll
+                for (int c = 0; c < 4; c++) x[q].v[c] = shoup_mul(x[q].v[c], f);
+            }
+        }
+        if (TO_GLOBAL) {
+            if (col_ok) {
+#pragma unroll
+                for (int q = 0; q < R; q++) x[q].store(g_out + (uint64_t)(base + (q << lowbits)) * g_out_step);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; q++) x[q].store(sm_out + (base + (q << lowbits)) * TILE_COLS + lane * 4);
+        }
+    }
+}
+
+// the K stages of one 2^K-point DIF as register rounds (remainder round first, like the other pass kernels);
+// FIRST_SRC says where round one reads (global / X / X through bit-reversed slots), the last round stores to global if
+// TO_GLOBAL, else everything ends in sm_work
+template <int K, int LC, int NT, int FIRST_SRC, bool TO_GLOBAL>
+__device__ __forceinline__ void mid_dif(const uint32_t* sm_first, uint32_t* sm_work, const uint2* sm_tw, const uint32_t* g_in, uint64_t g_in_step, uint32_t* g_out,
+                                        uint64_t g_out_step, bool col_ok, const uint2* fac_pre, const uint2* fac_post, int tid) {
+    constexpr int REM = K % 3;
+    constexpr int K1 = REM ? REM : 3;  // stages of the first round
+    static_assert(K >= 6 && K <= 8, "fused middle supports K = 6, 7, 8");
+    mid_round<K, LC, NT, K1, 0, FIRST_SRC, false>(sm_first, sm_work, sm_tw, g_in, g_in_step, nullptr, 0, col_ok, fac_pre, nullptr, tid);
+    __syncthreads();
+    if (K1 + 3 < K) {
+        mid_round<K, LC, NT, 3, K1, MID_FROM_SMEM, false>(sm_work, sm_work, sm_tw, nullptr, 0, nullptr, 0, col_ok, nullptr, nullptr, tid);
+        __syncthreads();
+    }
+    mid_round<K, LC, NT, 3, K - 3, MID_FROM_SMEM, TO_GLOBAL>(sm_work, sm_work, sm_tw, nullptr, 0, g_out, g_out_step, col_ok, nullptr, fac_post, tid);
+}
+
+template <int K, int LC, int NT, int CTAS>
+__global__ void __launch_bounds__(NT, CTAS) lde_mid_kernel(const MidParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int R = 1 << K, TILE_COLS = 1 << LC, LL = LC - 2;
+    uint32_t* X = smem;                                                      // [R][TILE_COLS] inverse result (bit-reversed slots)
+    uint32_t* Y = X + R * TILE_COLS;                                         // [R][TILE_COLS] forward work tile
+    uint2* tw_inv = reinterpret_cast<uint2*>(Y + R * TILE_COLS);             // [R/2]
+    uint2* tw_fwd = tw_inv + R / 2;                                          // [R/2]
+    uint2* twist = tw_fwd + R / 2;                                           // [cosets][R]
+    const int tid = threadIdx.x;
+    const int n = p.n, Lf = n - K;
+    const uint32_t col_tiles = (p.width + TILE_COLS - 1) >> LC;
+    const uint32_t ct = blockIdx.x % col_tiles;
+    const uint32_t j = blockIdx.x / col_tiles;                               // row tile of the inverse = high index of its last pass
+    const uint32_t q = bb::bitrev(j, Lf);                                    // low index of the first forward pass
+    const uint32_t col = (ct << LC) + (uint32_t)(tid & ((1 << LL) - 1)) * 4;
+    const bool col_ok = col < p.width;
+
+    for (int i = tid; i < R / 2; i += NT) {
+        tw_inv[i] = __ldg(p.tw_inv + i);
+        tw_fwd[i] = __ldg(p.tw_fwd + i);
+    }
+    for (int t = tid; t < R; t += NT) {
+        uint32_t w = bb::ONE;
+        if (q != 0) w = pow2level(p.tw_lo, p.tw_hi, (uint64_t)q * bb::bitrev((uint32_t)t, K));   // < 2^(n-K) * 2^K
+        for (int c = 0; c < p.cosets; c++) twist[c * R + t] = shoup_pair(bb::mul(w, pow2level(p.pre_lo[c], p.pre_hi[c], q)));
+    }
+    __syncthreads();
+
+    // inverse tail: rows j 2^K + slot, contiguous
+    mid_dif<K, LC, NT, MID_FROM_GLOBAL, false>(nullptr, X, tw_inv, p.in + ((uint64_t)j << K) * p.in_pitch + col, p.in_pitch, nullptr, 0, col_ok, nullptr, nullptr, tid);
+    __syncthreads();
+    // forward head of every coset: logical k lives in slot bitrev_K(k) of X; output slot t goes to row q + t 2^(n-K) of the block
+    for (int c = 0; c < p.cosets; c++) {
+        uint32_t* dst = p.out + (uint64_t)c * p.block_stride + (uint64_t)q * p.out_pitch + col;
+        mid_dif<K, LC, NT, MID_FROM_SMEM_BREV, true>(X, Y, tw_fwd, nullptr, 0, dst, (uint64_t)p.out_pitch << Lf, col_ok, p.sigma + c * R, twist + c * R, tid);
+        __syncthreads();  // Y is rewritten by the next coset's first round
+    }
+}
+
+// sigma[k] = base^k as a Shoup pair (base = s_c^(2^(n-K)), Montgomery form)
+__global__ void mid_sigma_kernel(uint2* out, uint32_t base, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = shoup_pair(bb::pow(base, i));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // TMA pass: the same K stages, as a persistent warp-specialised kernel.  One producer warp moves whole tiles between
 // HBM and shared memory with cp.async.bulk.tensor (one 4-D box per tile: {columns, low, t, high} of the strided row set)
 // through a 3-stage mbarrier ring; 256 consumer threads only ever touch shared memory, so butterflies of tile c overlap
