@@ -320,7 +320,7 @@ def main():
                 "peak_int_source": "564 products x 10 FMA-heavy-pipe clocks per warp-permutation at the SM clock sampled during the run (pipe rates measured in profiles/pipe_microbench_r01.txt)",
                 "note": "achieved/peak/frac are the HBM view the bench contract asks for; the kernel is bound by the 32-bit integer pipes (frac_int), its DRAM traffic equals its algorithmic bytes",
                 "lde": {"ms": round(lde_ms, 3), "achieved": round(b_lde / (lde_ms * 1e-3) / 1e9, 2), "frac": round(b_lde / (lde_ms * 1e-3) / 1e9 / peak, 4),
-                        "bound": "hbm+int32", "note": "9 pass sweeps of 8 B per element; per-pass DRAM rates and the copy-only ceiling of the same tile pattern are in profiles/ntt_lab_r02.txt"},
+                        "bound": "hbm+int32", "note": "6 pass sweeps of 8 B per element + the fused middle (4 B read + 8 B written per element); per-pass times in profiles/ntt_fused_mid_r02.txt, copy-only ceilings of the tile shapes in profiles/tile_copy_lab_r02.txt"},
                 "commit_ms": round(commit_ms, 3)}
 
     # ---- e2e: host buffers through the C ABI (pinned trace -> H2D -> LDE -> commit -> root D2H)
@@ -328,9 +328,9 @@ def main():
     if not args.no_e2e:
         host = torch.empty((n, w), dtype=torch.int32).pin_memory()
         ctx.check(lib.b200zk_mat_download(ctx.h, trace.h, host.data_ptr()))
-        # strip width of the pipeline: 32 columns (128-byte PCIe rows) balances copy and arithmetic on one GPU; when four or more
-        # GPUs share the host links the copy is the bottleneck and 256-byte rows (64 columns) move 16 % more per second
-        strip_cols = int(os.environ.get("B200ZK_STRIP", "0")) or (64 if world >= 4 and w % 64 == 0 else 0)
+        # strip width of the pipeline: 0 = the library's choice (32 columns for a blocking call, 64 for the asynchronous stream);
+        # B200ZK_STRIP=<cols> forces one (experiments)
+        strip_cols = int(os.environ.get("B200ZK_STRIP", "0"))
 
         def step_e2e():
             # the C-ABI call a host-side prover makes: host trace in, root out; the library pipelines the PCIe
@@ -339,17 +339,45 @@ def main():
             ctx.check(lib.b200zk_lde_commit_host(ctx.h, host.data_ptr(), n, w, b, shift, strip_cols, root.ctypes.data, C.byref(t)))
             lib.b200zk_tree_free(ctx.h, t)
 
-        step_e2e()
-        barrier()
-        k0, k1 = ev(), ev()
-        k0.record(stream)
-        for _ in range(args.steps):
-            step_e2e()
-        k1.record(stream)
-        barrier()
-        e_ms = torch.tensor([k0.elapsed_time(k1) / args.steps], device="cuda")
-        if world > 1:
-            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        def run_serial(k):
+            for _ in range(k):
+                step_e2e()
+
+        def run_stream(k):
+            # the same K commits as a stream, the way a prover walks the segments of a chunk proof: commit i + 1 is issued
+            # (b200zk_lde_commit_host_async) before the root of commit i is read back, so the first strip's transfer of one
+            # commit runs under the arithmetic of the previous one.  Every commit still moves its whole trace host -> device
+            # and its root device -> host inside the timed region; at most two are in flight.
+            pending = None
+            for _ in range(k):
+                t = C.c_void_p()
+                ctx.check(lib.b200zk_lde_commit_host_async(ctx.h, host.data_ptr(), n, w, b, shift, strip_cols, C.byref(t)))
+                if pending is not None:
+                    ctx.check(lib.b200zk_tree_root(ctx.h, pending, root.ctypes.data))
+                    lib.b200zk_tree_free(ctx.h, pending)
+                pending = t
+            ctx.check(lib.b200zk_tree_root(ctx.h, pending, root.ctypes.data))
+            lib.b200zk_tree_free(ctx.h, pending)
+
+        def timed(fn, warm=1):
+            fn(warm)  # untimed: the allocator reaches its steady state (the stream keeps two LDEs + trees alive at once)
+            barrier()
+            k0, k1 = ev(), ev()
+            k0.record(stream)
+            fn(args.steps)
+            k1.record(stream)
+            barrier()
+            t_ms = torch.tensor([k0.elapsed_time(k1) / args.steps], device="cuda")
+            if world > 1:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            return float(t_ms.item())
+
+        root_dev = root.copy()
+        serial_ms = timed(run_serial)
+        assert np.array_equal(root, root_dev), "host strip pipeline: root differs from the device-resident path"
+        stream_ms = timed(run_stream, warm=max(3, args.warmup))
+        assert np.array_equal(root, root_dev), "host strip pipeline (async): root differs from the device-resident path"
+        e_ms = torch.tensor([stream_ms], device="cuda")
         # what the host link gives every rank when all ranks copy at once: a plain contiguous pinned H2D copy (2 GiB), all
         # ranks together -- the bound of any e2e number at this N (the GPUs of one box share host memory and PCIe uplinks)
         chunk = host.view(-1)[: min(host.numel(), 1 << 29)]
@@ -368,7 +396,10 @@ def main():
         del dev_chunk
         link_gbs = float(link.item())
         e2e = {"value": round(world * (b_lde + b_commit) / (float(e_ms.item()) * 1e-3) / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": 4 * n * w, "d2h_bytes_per_step": 32,
-               "ms_per_step": round(float(e_ms.item()), 3), "strip_cols": strip_cols or 32,
+               "ms_per_step": round(float(e_ms.item()), 3), "strip_cols": strip_cols or 64,
+               "mode": "stream of K commits through b200zk_lde_commit_host_async, at most two in flight; every commit's H2D and root D2H inside the timed region",
+               "serial": {"value": round(world * (b_lde + b_commit) / (serial_ms * 1e-3) / 1e9, 3), "ms_per_step": round(serial_ms, 3), "strip_cols": strip_cols or 32,
+                          "mode": "one blocking b200zk_lde_commit_host call at a time"},
                "h2d_link_gbs_per_gpu": round(link_gbs, 1), "h2d_floor_ms": round(4 * n * w / link_gbs / 1e6, 1),
                "note": "h2d_link_gbs_per_gpu = slowest rank's plain contiguous pinned copy with all ranks copying at once; h2d_floor_ms = this step's input bytes at that rate"}
         del host

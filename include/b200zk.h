@@ -116,10 +116,16 @@ int b200zk_lde_commit(b200zk_ctx*, b200zk_mat* const* evals, uint32_t k, uint32_
                       const uint32_t* shifts_monty, uint32_t h_root[8], b200zk_tree** out);
 /* the same for ONE trace that still lives in host memory (pinned for full speed): the matrix is processed in column
  * strips so the host->device transfer of strip s+1 overlaps the LDE and leaf hashing of strip s (copy stream + compute
- * stream).  strip_cols = 0 picks the strip width; small or ragged inputs take the plain upload path.  Bit-identical to
- * b200zk_mat_upload + b200zk_lde_commit. */
+ * stream).  strip_cols = 0 picks the strip width (32 columns; 64 for the asynchronous form below, where only the copy rate
+ * matters).  Small or ragged inputs take the plain upload path.  Bit-identical to b200zk_mat_upload + b200zk_lde_commit. */
 int b200zk_lde_commit_host(b200zk_ctx*, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits,
                            uint32_t shift_monty, uint32_t strip_cols, uint32_t h_root[8], b200zk_tree** out);
+/* the same without waiting: returns once every copy and kernel is enqueued.  h_values must stay valid (and unmodified) until
+ * b200zk_tree_root(tree) or b200zk_ctx_sync returns.  Two calls may be in flight per context (their strip buffers alternate):
+ * issuing call i+1 before reading the root of call i hides the first strip's transfer under the previous call's arithmetic
+ * -- how a prover walks the segments of a chunk proof (crates/prover/src/prover/mod.rs:355-357 proves them one after another). */
+int b200zk_lde_commit_host_async(b200zk_ctx*, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits,
+                                 uint32_t shift_monty, uint32_t strip_cols, b200zk_tree** out);
 /* Mmcs::open_batch(index): rows_out = concatenation over matrices (original order) of row
  * index >> (log2 max_height - log2 height); path_out = depth x 8 siblings, bottom-up */
 int b200zk_merkle_open(b200zk_ctx*, const b200zk_tree*, uint64_t index, uint32_t* h_rows, uint32_t* h_path);

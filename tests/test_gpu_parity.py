@@ -367,6 +367,36 @@ def test_pcs_commit_lde_plus_mmcs(z, ctx):
     pcs.mmcs.verify_batch(root, [(l.shape[1], l.shape[0]) for l in ldes], 1234, rows, path)
 
 
+def test_commit_host_async_two_in_flight(z, ctx):
+    """b200zk_lde_commit_host_async: commits issued back to back (two in flight, alternating strip buffers) give the roots
+    of the blocking path, in any collection order, also when the shapes differ between calls (the strip buffers regrow)"""
+    import torch
+    pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=1), ctx)
+    shapes = [(14, 256), (14, 256), (15, 128), (14, 256), (16, 64)]
+    hosts, want = [], []
+    for i, (n, w) in enumerate(shapes):
+        tr = rnd((1 << n, w), 900 + i)
+        h = torch.from_numpy(tr.view(np.int32)).pin_memory()
+        hosts.append(h)
+        r, pd = pcs.commit([tr])
+        want.append(r)
+        pd.free()
+    pend = None
+    got = []
+    for h in hosts:
+        p = pcs.commit_host_async(h.data_ptr(), tuple(h.shape))
+        if pend is not None:
+            r, pd = pend.result()
+            got.append(r)
+            pd.free()
+        pend = p
+    r, pd = pend.result()
+    got.append(r)
+    pd.free()
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("n,w,strip", [(14, 256, 0), (14, 256, 32), (16, 64, 16), (15, 96, 0), (10, 256, 0), (14, 40, 0)])
 def test_commit_host_strip_pipeline_matches_plain_commit(z, ctx, n, w, strip):
     """b200zk_lde_commit_host (column-strip pipeline, H2D overlapped) == upload + lde_commit == oracle"""

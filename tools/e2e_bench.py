@@ -10,7 +10,7 @@ host.random_(0, 2013265921)
 ts = []
 for i in range(6):
     t0 = time.perf_counter()
-    root, pd = pcs.commit_host(None, host_ptr=host.data_ptr(), shape=(1 << 23, 256))
+    root, pd = pcs.commit_host(None, strip_cols=int(os.environ.get("B200ZK_STRIP", "0")), host_ptr=host.data_ptr(), shape=(1 << 23, 256))
     ts.append(time.perf_counter() - t0)
     pd.free()
-print(f"B200ZK_SPLIT_COPY={os.environ.get('B200ZK_SPLIT_COPY', 'default')}: e2e min {1e3 * min(ts[1:]):.1f} ms  all {[round(1e3 * t, 1) for t in ts]}  root {root[:2].tolist()}")
+print(f"B200ZK_STRIP={os.environ.get('B200ZK_STRIP', '0 (library schedule)')}: e2e min {1e3 * min(ts[1:]):.1f} ms  all {[round(1e3 * t, 1) for t in ts]}  root {root[:2].tolist()}")

@@ -70,6 +70,7 @@ _SIGS = {
     "b200zk_merkle_commit": (_int, [_p, C.POINTER(_p), _u32, _int, _p, C.POINTER(_p)]),
     "b200zk_lde_commit": (_int, [_p, C.POINTER(_p), _u32, _u32, _p, _p, C.POINTER(_p)]),
     "b200zk_lde_commit_host": (_int, [_p, _p, _u64, _u32, _u32, _u32, _u32, _p, C.POINTER(_p)]),
+    "b200zk_lde_commit_host_async": (_int, [_p, _p, _u64, _u32, _u32, _u32, _u32, C.POINTER(_p)]),
     "b200zk_merkle_open": (_int, [_p, _p, _u64, _p, _p]),
     "b200zk_merkle_open_many": (_int, [_p, _p, _p, _u32, _p, _p]),
     "b200zk_tree_depth": (_u32, [_p]),

@@ -45,7 +45,14 @@ struct b200zk_ctx {
     int num_sms = 148;
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), null if unavailable
     cudaStream_t copy_stream = nullptr;  // host->device strip copies of b200zk_lde_commit_host (created on first use)
-    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    // strip buffers of the host pipeline: two sets of two, dedicated (never handed to the allocator), so the copies of call
+    // i + 1 can run while call i is still computing out of the other set; one (copied, consumed) event pair per buffer
+    uint32_t* h_root_ring = nullptr;  // pinned, 64 slots of 8 words (roots of asynchronous commits)
+    uint32_t root_ring_next = 0;
+    uint32_t* strip_buf[4] = {};
+    size_t strip_buf_bytes = 0;
+    uint64_t strip_calls = 0;
+    cudaEvent_t ev_copied[4] = {}, ev_consumed[4] = {};
     std::unordered_multimap<size_t, void*> cache;   // freed blocks by (rounded) size, see dev_alloc
     std::unordered_map<void*, size_t> live;         // blocks handed out by dev_alloc
     size_t cache_bytes = 0, cache_cap = 0;
@@ -65,6 +72,10 @@ struct b200zk_tree {
     uint32_t* d_digests = nullptr;  // layer 0 | layer 1 | ... | root
     std::vector<uint64_t> layer_off;  // in digests
     mk::OpenMat* d_open = nullptr;
+    // asynchronous commits (b200zk_lde_commit_host_async): the root is copied to a pinned slot behind the last kernel and
+    // `ev_done` marks that point, so b200zk_tree_root waits for THIS tree only, not for commits enqueued after it
+    cudaEvent_t ev_done = nullptr;
+    uint32_t* h_root_slot = nullptr;
 };
 struct b200zk_chal {
     fri::ChalState* d = nullptr;
@@ -588,11 +599,14 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     cudaFree(ctx->tab);
     cudaFree(ctx->mid_sigma);
     cudaFree(ctx->d_small);
+    if (ctx->h_root_ring) cudaFreeHost(ctx->h_root_ring);
     if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 4; i++) {
             cudaEventDestroy(ctx->ev_copied[i]);
             cudaEventDestroy(ctx->ev_consumed[i]);
+            cudaFree(ctx->strip_buf[i]);
         }
     }
     cudaStreamDestroy(ctx->stream);
@@ -609,6 +623,12 @@ int b200zk_ctx_trim(b200zk_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     cache_flush(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+    for (int i = 0; i < 4; i++) {
+        cudaFree(ctx->strip_buf[i]);
+        ctx->strip_buf[i] = nullptr;
+    }
+    ctx->strip_buf_bytes = 0;
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
     CU(cudaMemPoolTrimTo(pool, 0));
@@ -1136,6 +1156,7 @@ int b200zk_compress_pairs(b200zk_ctx* ctx, const uint32_t* h_in, uint32_t* h_out
 void b200zk_tree_free(b200zk_ctx* ctx, b200zk_tree* t) {
     if (!t) return;
     if (ctx) cudaSetDevice(ctx->device);
+    if (t->ev_done) cudaEventDestroy(t->ev_done);
     dev_free(ctx, t->d_digests);
     dev_free(ctx, t->d_open);
     if (t->owns_mats)
@@ -1242,6 +1263,11 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
 int b200zk_tree_root(b200zk_ctx* ctx, const b200zk_tree* t, uint32_t h_root[8]) {
     if (!ctx) return B200ZK_ERR_ARG;
     if (!t || !h_root) return fail(ctx, B200ZK_ERR_ARG, "null tree/root");
+    if (t->ev_done) {  // asynchronous commit: wait for this tree's own completion point
+        CU(cudaEventSynchronize(t->ev_done));
+        memcpy(h_root, t->h_root_slot, 32);
+        return B200ZK_OK;
+    }
     CU(cudaMemcpyAsync(h_root, t->d_digests + 8 * (2 * t->max_h - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
@@ -1346,7 +1372,8 @@ namespace {
 struct StripJob {
     const uint32_t* h_values;
     uint64_t N;
-    uint32_t W, added_bits, shift, strip;
+    uint32_t W, added_bits, shift;
+    std::vector<uint32_t> strips;  // column count of every strip, in order (multiples of 16)
     b200zk_mat* lde;
 };
 int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
@@ -1355,55 +1382,79 @@ int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
     const uint64_t M = j.N << j.added_bits;
     if (!ctx->copy_stream) {
         CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 4; i++) {
             CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
         }
     }
-    uint32_t *sbuf[2] = {nullptr, nullptr}, *cap = nullptr;
-    int rc = dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[0]);
-    if (rc == B200ZK_OK) rc = dev_alloc(ctx, j.N * j.strip * 4, (void**)&sbuf[1]);
-    if (rc == B200ZK_OK) rc = dev_alloc(ctx, M * 32, (void**)&cap);
+    const uint32_t max_strip = *std::max_element(j.strips.begin(), j.strips.end());
+    const size_t need = j.N * max_strip * 4;
+    if (ctx->strip_buf_bytes < need) {  // grow: nothing may be in flight on the old buffers
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < 4; i++) {
+            cudaFree(ctx->strip_buf[i]);
+            ctx->strip_buf[i] = nullptr;
+        }
+        ctx->strip_buf_bytes = 0;
+        for (int i = 0; i < 4; i++) {
+            cudaError_t e = cudaMalloc((void**)&ctx->strip_buf[i], need);
+            if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try once more
+                cudaGetLastError();
+                cache_flush(ctx);
+                cudaStreamSynchronize(ctx->stream);
+                e = cudaMalloc((void**)&ctx->strip_buf[i], need);
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (int k = 0; k < 4; k++) {
+                    cudaFree(ctx->strip_buf[k]);
+                    ctx->strip_buf[k] = nullptr;
+                }
+                return fail(ctx, B200ZK_ERR_OOM, "strip buffers: " + std::string(cudaGetErrorString(e)));
+            }
+        }
+        ctx->strip_buf_bytes = need;
+    }
+    const int set = (int)(ctx->strip_calls++ & 1) * 2;  // consecutive calls alternate between the two buffer sets
+    uint32_t* cap = nullptr;
+    int rc = dev_alloc(ctx, M * 32, (void**)&cap);
     if (rc == B200ZK_OK) rc = lde_tables(ctx, n, j.added_bits, j.shift);
     auto cuda_ok = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess && rc == B200ZK_OK) rc = fail(ctx, B200ZK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
         return e == cudaSuccess;
     };
-    // the strip buffers come from the compute stream's pool: the copy stream may only touch them after this point
-    if (rc == B200ZK_OK) cuda_ok(cudaEventRecord(ctx->ev_consumed[0], ctx->stream), "event record");
-    if (rc == B200ZK_OK) cuda_ok(cudaEventRecord(ctx->ev_consumed[1], ctx->stream), "event record");
-    const uint32_t strips = j.W / j.strip;
+    const size_t strips = j.strips.size();
     bool copies_in_flight = false;
-    for (uint32_t s = 0; s < strips && rc == B200ZK_OK; s++) {
-        const int b = s & 1;
+    uint32_t col0 = 0;
+    for (size_t s = 0; s < strips && rc == B200ZK_OK; s++) {
+        const int b = set + (int)(s & 1);
+        uint32_t* sb = ctx->strip_buf[b];
+        const uint32_t sw = j.strips[s];
+        // the buffer's previous contents (two strips ago, or two calls ago) must have been consumed; a never-recorded event is a no-op
         if (!cuda_ok(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0), "stream wait")) break;
-        if (!cuda_ok(cudaMemcpy2DAsync(sbuf[b], (size_t)j.strip * 4, j.h_values + (size_t)s * j.strip, (size_t)j.W * 4, (size_t)j.strip * 4, j.N,
-                                       cudaMemcpyHostToDevice, ctx->copy_stream),
-                     "strip copy"))
-            break;
+        if (!cuda_ok(cudaMemcpy2DAsync(sb, (size_t)sw * 4, j.h_values + col0, (size_t)j.W * 4, (size_t)sw * 4, j.N, cudaMemcpyHostToDevice, ctx->copy_stream), "strip copy")) break;
         copies_in_flight = true;
         if (!cuda_ok(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream), "event record")) break;
         if (!cuda_ok(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0), "stream wait")) break;
-        rc = lde_core(ctx, sbuf[b], j.strip, n, j.strip, j.added_bits, j.lde->d + (size_t)s * j.strip, j.W, nullptr, /*scratch=*/sbuf[b], j.strip);
+        rc = lde_core(ctx, sb, sw, n, sw, j.added_bits, j.lde->d + col0, j.W, nullptr, /*scratch=*/sb, sw);
         if (rc != B200ZK_OK) break;
         if (!cuda_ok(cudaEventRecord(ctx->ev_consumed[b], ctx->stream), "event record")) break;
-        mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, ctx->stream>>>(j.lde->d, j.W, s * j.strip, j.strip, M, cap, s == 0, s + 1 == strips,
-                                                                                           d_digests);
+        mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, ctx->stream>>>(j.lde->d, j.W, col0, sw, M, cap, s == 0, s + 1 == strips, d_digests);
         ctx->launches++;
         cuda_ok(cudaGetLastError(), "leaf_absorb_strip launch");
+        col0 += sw;
     }
     // on an error path copies from the caller's h_values may still be queued on the copy stream: drain it before the
     // buffers go back to the allocator and before the caller is told it may release the host memory
     if (rc != B200ZK_OK && copies_in_flight) cudaStreamSynchronize(ctx->copy_stream);
-    dev_free(ctx, sbuf[0]);
-    dev_free(ctx, sbuf[1]);
     dev_free(ctx, cap);
     return rc;
 }
 }  // namespace
 
-int b200zk_lde_commit_host(b200zk_ctx* ctx, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits, uint32_t shift, uint32_t strip_cols,
-                           uint32_t h_root[8], b200zk_tree** out) {
+static int lde_commit_host_impl(b200zk_ctx* ctx, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits, uint32_t shift, uint32_t strip_cols,
+                                uint32_t h_root[8], b200zk_tree** out, bool async) {
     if (!ctx || !out) return B200ZK_ERR_ARG;
     *out = nullptr;
     if (!h_values) return fail(ctx, B200ZK_ERR_ARG, "null host pointer");
@@ -1412,22 +1463,53 @@ int b200zk_lde_commit_host(b200zk_ctx* ctx, const uint32_t* h_values, uint64_t r
     if (n + (int)added_bits > MAX_LOG) return fail(ctx, B200ZK_ERR_SHAPE, "size exceeds the two-adicity of BabyBear (2^27)");
     if (shift == 0 || shift >= bb::P) return fail(ctx, B200ZK_ERR_ARG, "shift must be a non-zero field element");
     CU(cudaSetDevice(ctx->device));
-    uint32_t strip = strip_cols ? strip_cols : 32;  // measured best on B200 + PCIe gen5 (16: 341 ms, 32: 222 ms, 64: 233 ms, 128: 270 ms at 2^23 x 256)
-    while (strip > 16 && (width % strip || width / strip < 2)) strip >>= 1;
-    const bool pipelined = n >= 1 && added_bits >= 1 && width % strip == 0 && strip % 16 == 0 && width / strip >= 2 && rows * (uint64_t)width >= (1ull << 22);
-    if (!pipelined) {  // small or ragged: upload, extend, commit
+    // Strip width.  A strip row is one DMA segment: 128-byte segments (32 columns) reach ~86 % of the contiguous copy rate,
+    // 256-byte segments (64 columns) all of it, 64-byte segments under half.  Inside ONE blocking call the first strip's
+    // transfer and the last strip's arithmetic are exposed, which favours narrow strips (measured at 2^23 x 256, r01: 16: 341 ms,
+    // 32: 222 ms, 64: 233 ms, 128: 270 ms; r02: 32: 203 ms, 64: 205 ms).  A stream of asynchronous calls hides both ends under
+    // the neighbouring calls, so only the copy rate matters: 64.  (A graded schedule 16 16 32 64 64 32 16 16 was tried in r02
+    // and is slower than either, 227 ms: with copy and arithmetic this close to each other per column, any strip whose copy
+    // is longer than the previous strip's arithmetic stalls the compute stream -- profiles/e2e_strip_schedule_r02.txt.)
+    std::vector<uint32_t> sched;
+    {
+        uint32_t strip = strip_cols ? strip_cols : (async ? 64 : 32);
+        while (strip > 16 && (width % strip || width / strip < 2)) strip >>= 1;
+        if (width % strip == 0 && strip % 16 == 0 && width / strip >= 2) sched.assign(width / strip, strip);
+    }
+    const bool pipelined = n >= 1 && added_bits >= 1 && !sched.empty() && rows * (uint64_t)width >= (1ull << 22);
+    if (!pipelined) {  // small or ragged: upload (synchronous: h_values is free again on return), extend, commit
         b200zk_mat* m = nullptr;
         TRY(b200zk_mat_upload(ctx, h_values, rows, width, &m));
         b200zk_mat* arr[1] = {m};
-        int rc = b200zk_lde_commit(ctx, arr, 1, added_bits, &shift, h_root, out);
+        int rc = b200zk_lde_commit(ctx, arr, 1, added_bits, &shift, async ? nullptr : h_root, out);
         b200zk_mat_free(ctx, m);
         return rc;
     }
     b200zk_mat* lde = nullptr;
     TRY(b200zk_mat_alloc(ctx, rows << added_bits, width, &lde));
-    StripJob job{h_values, rows, width, added_bits, shift, strip, lde};
+    StripJob job{h_values, rows, width, added_bits, shift, sched, lde};
     b200zk_mat* arr[1] = {lde};
     int rc = commit_async(ctx, arr, 1, /*take=*/1, out, strip_pipeline, &job);
+    if (rc == B200ZK_OK && async) {  // everything is enqueued; b200zk_tree_root waits for this tree's completion point
+        b200zk_tree* t = *out;
+        cudaError_t e = cudaSuccess;
+        if (!ctx->h_root_ring) e = cudaMallocHost((void**)&ctx->h_root_ring, 64 * 32);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) {
+            t->h_root_slot = ctx->h_root_ring + 8 * (ctx->root_ring_next++ & 63);
+            e = cudaMemcpyAsync(t->h_root_slot, t->d_digests + 8 * (2 * t->max_h - 2), 32, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(t->ev_done, ctx->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaStreamSynchronize(ctx->stream);  // h_values may be released by the caller after an error
+            if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+            b200zk_tree_free(ctx, t);
+            *out = nullptr;
+            return fail(ctx, B200ZK_ERR_CUDA, std::string("async commit: ") + cudaGetErrorString(e));
+        }
+        return rc;
+    }
     if (rc == B200ZK_OK && h_root) rc = b200zk_tree_root(ctx, *out, h_root);
     else if (rc == B200ZK_OK) rc = b200zk_ctx_sync(ctx);  // h_values must stay valid until the copies are done
     if (rc != B200ZK_OK) {
@@ -1439,6 +1521,18 @@ int b200zk_lde_commit_host(b200zk_ctx* ctx, const uint32_t* h_values, uint64_t r
         }
     }
     return rc;
+}
+
+int b200zk_lde_commit_host(b200zk_ctx* ctx, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits, uint32_t shift, uint32_t strip_cols,
+                           uint32_t h_root[8], b200zk_tree** out) {
+    return lde_commit_host_impl(ctx, h_values, rows, width, added_bits, shift, strip_cols, h_root, out, false);
+}
+// The same, returning as soon as the copies and kernels are enqueued: a prover that commits one trace after another (the
+// segments of a chunk proof) issues call i + 1 before it reads the root of call i, so the first strip's transfer -- the one
+// part of the pipeline nothing can hide inside a single call -- runs under the previous call's arithmetic.
+int b200zk_lde_commit_host_async(b200zk_ctx* ctx, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits, uint32_t shift,
+                                 uint32_t strip_cols, b200zk_tree** out) {
+    return lde_commit_host_impl(ctx, h_values, rows, width, added_bits, shift, strip_cols, nullptr, out, true);
 }
 
 uint32_t b200zk_tree_depth(const b200zk_tree* t) { return t ? t->depth : 0; }

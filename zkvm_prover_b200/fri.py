@@ -120,6 +120,20 @@ def commit_phase(config: FriConfig, inputs, challenger: DuplexChallenger | None,
             lib.b200zk_dev_free(ctx.h, d)
 
 
+class PendingCommit:
+    """a commit whose copies and kernels are enqueued but not waited for (TwoAdicFriPcs.commit_host_async)"""
+
+    def __init__(self, ctx, tree):
+        self.ctx, self.tree = ctx, tree
+
+    def result(self):
+        root = np.empty(DIGEST, np.uint32)
+        self.ctx.check(self.ctx.lib.b200zk_tree_root(self.ctx.h, self.tree, root.ctypes.data))
+        n = int(self.ctx.lib.b200zk_tree_num_mats(self.tree))
+        ldes = [DeviceMatrix(self.ctx, C.c_void_p(self.ctx.lib.b200zk_tree_mat(self.tree, i)), False) for i in range(n)]
+        return root, ProverData(self.ctx, self.tree, ldes)
+
+
 class TwoAdicFriPcs:
     """The commit half of p3_fri::TwoAdicFriPcs: `commit(evaluations)` = coset LDE of every trace matrix with
     shift GENERATOR / domain_shift (= 31 for the shift-1 trace domains OpenVM uses), rows kept in
@@ -163,6 +177,14 @@ class TwoAdicFriPcs:
         n = int(self.ctx.lib.b200zk_tree_num_mats(t))
         ldes = [DeviceMatrix(self.ctx, C.c_void_p(self.ctx.lib.b200zk_tree_mat(t, i)), False) for i in range(n)]
         return root, ProverData(self.ctx, t, ldes)
+
+    def commit_host_async(self, host_ptr: int, shape, strip_cols: int = 0) -> "PendingCommit":
+        """b200zk_lde_commit_host_async: enqueue the whole strip pipeline and return; `result()` of the handle waits and
+        gives (root, ProverData).  The host buffer must stay untouched until then.  Two may be in flight per context: a
+        prover walking the segments of a chunk proof issues segment i + 1 before collecting segment i."""
+        t = C.c_void_p()
+        self.ctx.check(self.ctx.lib.b200zk_lde_commit_host_async(self.ctx.h, host_ptr, shape[0], shape[1], self.config.log_blowup, GENERATOR_MONTY, strip_cols, C.byref(t)))
+        return PendingCommit(self.ctx, t)
 
     # ---- open phase (SURVEY 8(f)-1): the data-parallel body of TwoAdicFriPcs::open, LDEs stay on the device
     def inv_denominators(self, log_height: int, point) -> DeviceBuffer:
