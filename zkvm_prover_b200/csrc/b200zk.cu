@@ -47,6 +47,8 @@ struct b200zk_ctx {
     cudaStream_t copy_stream = nullptr;  // host->device strip copies of b200zk_lde_commit_host (created on first use)
     // strip buffers of the host pipeline: two sets of two, dedicated (never handed to the allocator), so the copies of call
     // i + 1 can run while call i is still computing out of the other set; one (copied, consumed) event pair per buffer
+    cudaStream_t hash_stream = nullptr;  // experiment (B200ZK_HASH_STREAM=1): strip absorbs run here, under the next strip's LDE
+    cudaEvent_t ev_lde[8] = {}, ev_abs = nullptr;
     uint32_t* h_root_ring = nullptr;  // pinned, 64 slots of 8 words (roots of asynchronous commits)
     uint32_t root_ring_next = 0;
     uint32_t* strip_buf[4] = {};
@@ -388,7 +390,7 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
         p.rt_base = 0;
         {
             const char* e = getenv("B200ZK_NTT_PREFETCH");  // experiment knob: CTAs of look-ahead (0 disables)
-            p.prefetch_dist = e ? (uint32_t)atoi(e) : 148u; // measured best look-ahead (profiles/ntt_tuning_r01.txt)
+            p.prefetch_dist = e ? (uint32_t)atoi(e) : 148u; // measured best look-ahead of pass_kernel (profiles/ntt_tuning_r01.txt)
         }
         const uint64_t R = 1ull << K;
         // Passes that multiply by per-row factors (coset prescale, inter-pass twist: every pass but the last one of a
@@ -403,6 +405,10 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             const uint64_t tiles = ((1ull << n) >> K) * ((width + (1u << lcd) - 1) >> lcd);
             if (tiles > 0x7fffffffull) return fail(ctx, B200ZK_ERR_SHAPE, "too many tiles for one launch");
             const size_t dsm = ((size_t)R << lcd) * 4 + (R / 2) * 8 + 2 * R * 8;
+            {
+                const char* e = getenv("B200ZK_DIRECT_PREFETCH");  // experiment knob: look-ahead of the direct kernel in CTAs (0 disables)
+                p.prefetch_dist = e ? (uint32_t)atoi(e) : (uint32_t)ctx->num_sms;  // measured (profiles/ntt_fused_mid_r02.txt): 148: 36.3 ms, 0: 36.7, 592: 36.8, 1184: 38.8
+            }
             {
                 PassTimer tm(ctx, inverse ? (p.out_natural ? "inv-scat" : "inv") : (p.pre_lo ? "fwd-pre" : "fwd"), n, s0, K, width);
                 if (K == 8) ntt::pass_kernel_direct<8, 5><<<(uint32_t)tiles, ntt::DIRECT_THREADS, dsm, ctx->stream>>>(p);
@@ -541,7 +547,11 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
     b200zk_ctx* ctx = new (std::nothrow) b200zk_ctx();
     if (!ctx) return B200ZK_ERR_OOM;
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    int prio_least = 0, prio_greatest = 0;
+    cudaSetDevice(device);
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    cudaGetLastError();
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
         delete ctx;
         return B200ZK_ERR_CUDA;
     }
@@ -600,6 +610,11 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     cudaFree(ctx->mid_sigma);
     cudaFree(ctx->d_small);
     if (ctx->h_root_ring) cudaFreeHost(ctx->h_root_ring);
+    if (ctx->hash_stream) {
+        cudaStreamDestroy(ctx->hash_stream);
+        for (auto& e : ctx->ev_lde) cudaEventDestroy(e);
+        cudaEventDestroy(ctx->ev_abs);
+    }
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
@@ -838,6 +853,10 @@ int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, ui
             mp.width = width;
             mp.n = n;
             mp.cosets = (int)C;
+            {
+                const char* e = getenv("B200ZK_MID_PREFETCH");  // experiment knob: look-ahead of the fused middle in CTAs (0 disables)
+                mp.prefetch_dist = e ? (uint32_t)atoi(e) : 0u;
+            }
             mp.tw_inv = ctx->tw_local[1][km];
             mp.tw_fwd = ctx->tw_local[0][km];
             mp.tw_lo = ctx->tw_lo[n];
@@ -1416,6 +1435,17 @@ int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
         }
         ctx->strip_buf_bytes = need;
     }
+    static const bool hash_side = [] {
+        const char* e = getenv("B200ZK_HASH_STREAM");  // experiment knob: 1 = absorb strip s on a second (low-priority) stream while strip s+1 is extended
+        return e && atoi(e) != 0;
+    }();
+    if (hash_side && !ctx->hash_stream) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        CU(cudaStreamCreateWithPriority(&ctx->hash_stream, cudaStreamNonBlocking, least));
+        for (auto& e : ctx->ev_lde) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_abs, cudaEventDisableTiming));
+    }
     const int set = (int)(ctx->strip_calls++ & 1) * 2;  // consecutive calls alternate between the two buffer sets
     uint32_t* cap = nullptr;
     int rc = dev_alloc(ctx, M * 32, (void**)&cap);
@@ -1440,10 +1470,20 @@ int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
         rc = lde_core(ctx, sb, sw, n, sw, j.added_bits, j.lde->d + col0, j.W, nullptr, /*scratch=*/sb, sw);
         if (rc != B200ZK_OK) break;
         if (!cuda_ok(cudaEventRecord(ctx->ev_consumed[b], ctx->stream), "event record")) break;
-        mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, ctx->stream>>>(j.lde->d, j.W, col0, sw, M, cap, s == 0, s + 1 == strips, d_digests);
+        cudaStream_t hs = ctx->stream;
+        if (hash_side) {
+            hs = ctx->hash_stream;
+            if (!cuda_ok(cudaEventRecord(ctx->ev_lde[s & 7], ctx->stream), "event record")) break;
+            if (!cuda_ok(cudaStreamWaitEvent(hs, ctx->ev_lde[s & 7], 0), "stream wait")) break;
+        }
+        mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, hs>>>(j.lde->d, j.W, col0, sw, M, cap, s == 0, s + 1 == strips, d_digests);
         ctx->launches++;
         cuda_ok(cudaGetLastError(), "leaf_absorb_strip launch");
         col0 += sw;
+    }
+    if (hash_side && rc == B200ZK_OK) {  // the tree is built on the main stream, behind the last absorb
+        cuda_ok(cudaEventRecord(ctx->ev_abs, ctx->hash_stream), "event record");
+        cuda_ok(cudaStreamWaitEvent(ctx->stream, ctx->ev_abs, 0), "stream wait");
     }
     // on an error path copies from the caller's h_values may still be queued on the copy stream: drain it before the
     // buffers go back to the allocator and before the caller is told it may release the host memory

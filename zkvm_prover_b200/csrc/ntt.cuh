@@ -406,6 +406,21 @@ __global__ void __launch_bounds__(DIRECT_THREADS, NTT_DIRECT_CTAS) pass_kernel_d
     const uint2* fac_pre = p.pre_lo ? sm_fac : nullptr;
     const uint2* fac_post = need_twist ? sm_fac + R : nullptr;
 
+    // L2 prefetch of the tile the CTA scheduled `prefetch_dist` blocks later will load (one 128-byte line per row and 32 columns):
+    // when that CTA starts, its first-round loads see L2 latency instead of HBM latency (ncu r02: long_scoreboard is this
+    // kernel's top stall while DRAM runs at 45 %)
+    if (p.prefetch_dist && blockIdx.x + p.prefetch_dist < gridDim.x) {
+        const uint32_t fb = blockIdx.x + p.prefetch_dist;
+        const uint32_t fct = fb % col_tiles;
+        const uint64_t frt = fb / col_tiles;
+        const uint64_t frow_base = ((frt >> L) << (n - s0)) + (frt & ((1ull << L) - 1));
+        constexpr int LINES = TILE_COLS / 32 > 0 ? TILE_COLS / 32 : 1;
+        for (int i = tid; i < R * LINES; i += DIRECT_THREADS) {
+            const int t = i / LINES, ln = i % LINES;
+            const uint32_t c = (fct << LC) + ln * 32;
+            if (c < p.width) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + (frow_base + ((uint64_t)t << L)) * p.in_pitch + c));
+        }
+    }
     // tables first (their L2 look-ups overlap the first round's global loads, which do not depend on them until the
     // barrier below); R <= 256 rows, one per thread
     for (int i = tid; i < R / 2; i += DIRECT_THREADS) sm_tw[i] = __ldg(p.tw_local + i);
@@ -462,6 +477,7 @@ struct MidParams {
     uint64_t block_stride;    // elements between coset blocks
     uint32_t in_pitch, out_pitch, width;
     int n, cosets;
+    uint32_t prefetch_dist;   // CTAs of look-ahead of the L2 prefetch (0: none)
     const uint2* tw_inv;      // 2^(K-1) local inverse roots (Shoup pairs)
     const uint2* tw_fwd;      // 2^(K-1) local forward roots
     const uint32_t* tw_lo;    // w_N^i, two-level
@@ -595,6 +611,16 @@ __global__ void __launch_bounds__(NT, CTAS) lde_mid_kernel(const MidParams p) {
     const uint32_t col = (ct << LC) + (uint32_t)(tid & ((1 << LL) - 1)) * 4;
     const bool col_ok = col < p.width;
 
+    if (p.prefetch_dist && blockIdx.x + p.prefetch_dist < gridDim.x) {  // L2 prefetch of a later CTA's tile (see pass_kernel_direct)
+        const uint32_t fb = blockIdx.x + p.prefetch_dist;
+        const uint32_t fct = fb % col_tiles, fj = fb / col_tiles;
+        constexpr int LINES = TILE_COLS / 32 > 0 ? TILE_COLS / 32 : 1;
+        for (int i = tid; i < R * LINES; i += NT) {
+            const int t = i / LINES, ln = i % LINES;
+            const uint32_t c = (fct << LC) + ln * 32;
+            if (c < p.width) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + (((uint64_t)fj << K) + t) * p.in_pitch + c));
+        }
+    }
     for (int i = tid; i < R / 2; i += NT) {
         tw_inv[i] = __ldg(p.tw_inv + i);
         tw_fwd[i] = __ldg(p.tw_fwd + i);
