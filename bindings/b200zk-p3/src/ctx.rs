@@ -137,6 +137,13 @@ impl Tree {
     pub fn total_width(&self) -> usize {
         unsafe { sys::b200zk_tree_total_width(self.raw) as usize }
     }
+    /// The root digest (`b200zk_tree_root`).  For a tree from `b200zk_lde_commit_host_async` this is the collection point:
+    /// it waits for that commit only, not for commits issued after it.
+    pub fn root(&self) -> Result<crate::Digest, Error> {
+        let mut r = [F::default(); 8];
+        self.ctx.check(unsafe { sys::b200zk_tree_root(self.ctx.raw, self.raw, r.as_mut_ptr() as *mut u32) })?;
+        Ok(r)
+    }
     /// Borrowed handle of committed matrix `i` (original order); lives as long as the tree.
     pub fn matrix(&self, i: usize) -> DeviceMatrix {
         let raw = unsafe { sys::b200zk_tree_mat(self.raw, i as u32) } as *mut sys::b200zk_mat;
