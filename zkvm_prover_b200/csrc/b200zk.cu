@@ -815,8 +815,14 @@ int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, ui
                       (!scratch || ((uintptr_t)scratch % 16 == 0 && scratch_pitch % 4 == 0));
     std::vector<int> rest;
     const int km = n >= 6 ? mid_plan(n, &rest) : 0;
-    if (mid_enabled() && vec4 && ctx->encode_tiled && tma_enabled() && n >= 6 && C <= (uint32_t)ntt::MID_MAX_COSETS && !(scatter && rest.empty()) &&
-        (N >> km) * ((width + (1u << (13 - km)) - 1) >> (13 - km)) <= 0x7fffffffull) {
+    bool fused = mid_enabled() && vec4 && ctx->encode_tiled && tma_enabled() && n >= 6 && C <= (uint32_t)ntt::MID_MAX_COSETS && !(scatter && rest.empty()) &&
+                 (N >> km) * ((width + (1u << (12 - std::min(km, 7))) - 1) >> (12 - std::min(km, 7))) <= 0x7fffffffull;
+    uint32_t* tmp = nullptr;
+    if (fused && !rest.empty() && !scratch && dev_alloc(ctx, N * width * 4, (void**)&tmp) != B200ZK_OK) {
+        fused = false;  // no room for the N x W scratch (e.g. 2^24 x 512 next to other residents): the unfused form needs none
+        ctx->err.clear();
+    }
+    if (fused) {
         const uint64_t R = 1ull << km;
         const int lcm = 13 - km;
         std::vector<int> inv_plan = rest, fwd_plan = {km};
@@ -827,7 +833,6 @@ int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, ui
         TRY(ensure_local(ctx, 1, km));
         if (ctx->mid_sigma_pairs < C * R) return fail(ctx, B200ZK_ERR_ARG, "internal: lde_tables was not run for this shape");
         ntt::MidParams mp{};
-        uint32_t* tmp = nullptr;
         const uint32_t* mid_in = src;
         uint32_t mid_pitch = src_pitch;
         int rc = B200ZK_OK;
@@ -835,7 +840,6 @@ int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, ui
             uint32_t* work = scratch;
             uint32_t wpitch = scratch_pitch ? scratch_pitch : width;
             if (!work) {
-                rc = dev_alloc(ctx, N * width * 4, (void**)&tmp);
                 work = tmp;
                 wpitch = width;
             }
