@@ -532,6 +532,9 @@ static int configure_kernels(int max_smem_optin) {
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return B200ZK_ERR_CUDA;
     for (int i = 0; i < 11; i++)
         if (cudaFuncSetAttribute(big[i], cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) return B200ZK_ERR_CUDA;
+    if (const char* e = getenv("B200ZK_HASH_STREAM"))  // co-residency experiment: the absorb kernel asks for the NTT kernels' carve-out
+        if (atoi(e) == 2 && cudaFuncSetAttribute((const void*)mk::leaf_absorb_strip_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+            return B200ZK_ERR_CUDA;
     return B200ZK_OK;
 }
 
@@ -1439,10 +1442,17 @@ int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
         }
         ctx->strip_buf_bytes = need;
     }
-    static const bool hash_side = [] {
-        const char* e = getenv("B200ZK_HASH_STREAM");  // experiment knob: 1 = absorb strip s on a second (low-priority) stream while strip s+1 is extended
-        return e && atoi(e) != 0;
+    static const int hash_mode = [] {
+        // experiment knob: 1 = absorb strip s on a second (low-priority) stream while strip s+1 is extended; 2 = the same with a small
+        // persistent absorb grid (B200ZK_HASH_CTAS per SM, default 2) so that the NTT kernels find room on every SM next to it
+        const char* e = getenv("B200ZK_HASH_STREAM");
+        return e ? atoi(e) : 0;
     }();
+    static const int hash_ctas = [] {
+        const char* e = getenv("B200ZK_HASH_CTAS");
+        return e ? std::max(1, atoi(e)) : 2;
+    }();
+    const bool hash_side = hash_mode != 0;
     if (hash_side && !ctx->hash_stream) {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
@@ -1480,7 +1490,8 @@ int strip_pipeline(b200zk_ctx* ctx, void* user, uint32_t* d_digests) {
             if (!cuda_ok(cudaEventRecord(ctx->ev_lde[s & 7], ctx->stream), "event record")) break;
             if (!cuda_ok(cudaStreamWaitEvent(hs, ctx->ev_lde[s & 7], 0), "stream wait")) break;
         }
-        mk::leaf_absorb_strip_kernel<<<(uint32_t)((M + 255) / 256), 256, 0, hs>>>(j.lde->d, j.W, col0, sw, M, cap, s == 0, s + 1 == strips, d_digests);
+        const uint32_t agrid = hash_mode == 2 ? (uint32_t)std::min<uint64_t>((M + 255) / 256, (uint64_t)hash_ctas * ctx->num_sms) : (uint32_t)((M + 255) / 256);
+        mk::leaf_absorb_strip_kernel<<<agrid, 256, 0, hs>>>(j.lde->d, j.W, col0, sw, M, cap, s == 0, s + 1 == strips, d_digests);
         ctx->launches++;
         cuda_ok(cudaGetLastError(), "leaf_absorb_strip launch");
         col0 += sw;

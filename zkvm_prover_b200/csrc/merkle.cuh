@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(256, MK_FAST_MINB) leaf_hash_fast_kernel(const
 // rate half is overwritten by the next chunk.  `cap` is rows x 8; the last strip writes the digest.
 __global__ void __launch_bounds__(256, MK_FAST_MINB) leaf_absorb_strip_kernel(const uint32_t* __restrict__ mat, uint32_t pitch, uint32_t col0, uint32_t cols, uint64_t rows,
                                                                 uint32_t* __restrict__ cap, int first, int last, uint32_t* __restrict__ digests) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
+    // grid-stride over the rows: with the usual one-thread-per-row grid the loop runs once; a small persistent grid (a couple of
+    // CTAs per SM) leaves registers and shared memory of every SM free for the NTT kernels of the next strip (B200ZK_HASH_STREAM=2)
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t st[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) st[k] = 0;
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(256, MK_FAST_MINB) leaf_absorb_strip_kernel(co
         uint4* cp = reinterpret_cast<uint4*>(cap + 8 * i);
         cp[0] = make_uint4(st[8], st[9], st[10], st[11]);
         cp[1] = make_uint4(st[12], st[13], st[14], st[15]);
+    }
     }
 }
 
