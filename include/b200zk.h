@@ -219,6 +219,10 @@ int b200zk_peer_free(b200zk_ctx*, void* d);
  * Synchronise the stream and the ranks before reading the receive buffer. */
 int b200zk_coset_lde_scatter(b200zk_ctx*, const b200zk_mat* evals, uint32_t added_bits, uint32_t shift_monty, uint32_t world, uint32_t rank,
                              uint32_t* const* d_recv);
+/* the same with the owner's receive buffer laid out as ONE row-major [M / world][world * width] matrix (this rank's columns at
+ * column offset rank * width), so the owner commits a single wide matrix (the fast leaf-hash path) instead of `world` narrow ones */
+int b200zk_coset_lde_scatter_rows(b200zk_ctx*, const b200zk_mat* evals, uint32_t added_bits, uint32_t shift_monty,
+                                  uint32_t world, uint32_t rank, uint32_t* const* d_recv);
 
 /* ---- raw device memory helpers for FFI users that do not bring their own allocator ------------------ */
 int b200zk_dev_alloc(b200zk_ctx*, uint64_t bytes, void** d_out);

@@ -31,10 +31,10 @@ def _worker(rank, world, port, n, w, out_dir):
         np.save(os.path.join(out_dir, f"root{rank}.npy"), root)
         # the same with the exchange fused into the last NTT pass (TMA stores into the peer's receive buffer), twice on one mapping
         exch = D.PeerExchange(ctx, 2 * n, wg)
-        for rep in range(2):
-            root2, cap2 = D.sharded_lde_commit_p2p(ctx, ctx.upload(local), 1, z.GENERATOR_MONTY, exch)
+        for rep in range(4):  # both receive layouts (one wide matrix per owner / one slot per sender), twice each on one mapping
+            root2, cap2 = D.sharded_lde_commit_p2p(ctx, ctx.upload(local), 1, z.GENERATOR_MONTY, exch, rows_layout=rep % 2 == 0)
             assert np.array_equal(cap2, cap), (rank, rep)
-            np.save(os.path.join(out_dir, f"p2p{rank}.npy"), root2)
+            np.save(os.path.join(out_dir, f"p2p{rank}_{rep % 2}.npy"), root2)
         exch.close()
         if rank == 0:  # single-GPU reference on the same device
             pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=1), ctx)
@@ -54,4 +54,5 @@ def test_sharded_commit_on_gpus(tmp_path):
     single = np.load(tmp_path / "single.npy")
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"root{r}.npy"), single)
-        assert np.array_equal(np.load(tmp_path / f"p2p{r}.npy"), single)
+        assert np.array_equal(np.load(tmp_path / f"p2p{r}_0.npy"), single)
+        assert np.array_equal(np.load(tmp_path / f"p2p{r}_1.npy"), single)

@@ -106,6 +106,7 @@ _SIGS = {
     "b200zk_peer_close": (_int, [_p, _p]),
     "b200zk_peer_free": (_int, [_p, _p]),
     "b200zk_coset_lde_scatter": (_int, [_p, _p, _u32, _u32, _u32, _u32, _p]),
+    "b200zk_coset_lde_scatter_rows": (_int, [_p, _p, _u32, _u32, _u32, _u32, _p]),
     "b200zk_ext_powers": (_int, [_p, _p, _u32, _p]),
     "b200zk_open_reduce": (_int, [_p, _p, _u32, _u32, _p, _p, _p, _p, _u32, _p, _p]),
     "b200zk_dev_download": (_int, [_p, _p, _p, _u64]),

@@ -11,6 +11,8 @@ from an `ops` object: `GpuOps` (the CUDA library) in production; the CPU tests i
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -171,6 +173,10 @@ class PeerExchange:
         """my row block of `sender`'s columns: an (mg, wg) matrix inside my receive buffer"""
         return self.ctx.wrap(self.own + 4 * sender * self.mg * self.wg, self.mg, self.wg)
 
+    def matrix(self):
+        """the rows layout (b200zk_coset_lde_scatter_rows): my whole row block as ONE (mg, world * wg) matrix"""
+        return self.ctx.wrap(self.own, self.mg, self.world * self.wg)
+
     def close(self):
         if getattr(self, "ptrs", None):
             dist.barrier(self.group)   # nobody may still be storing into a buffer that is about to go away
@@ -182,31 +188,52 @@ class PeerExchange:
             self.ptrs = None
 
 
-def sharded_lde_commit_p2p(ctx, local_cols, added_bits: int, shift: int, exch: PeerExchange | None = None, group=None):
+def sharded_lde_commit_p2p(ctx, local_cols, added_bits: int, shift: int, exch: PeerExchange | None = None, group=None, rows_layout: bool = True):
     """`sharded_lde_commit` with the exchange fused into the transform: b200zk_coset_lde_scatter stores the finished tiles of the last
     NTT pass directly into the owner's receive buffer (TMA over a peer mapping), so there is no all-to-all and no staging copy.
-    local_cols: this rank's column shard as a DeviceMatrix (N x wg).  Returns (root, cap) like `sharded_lde_commit`."""
+    local_cols: this rank's column shard as a DeviceMatrix (N x wg).  Returns (root, cap) like `sharded_lde_commit`.
+    rows_layout (default): the receive buffer is one row-major (M / world) x W matrix (every sender stores its columns at its own
+    column offset), so the owner hashes ONE wide matrix with the fast leaf kernel; False keeps one (M / world) x wg slot per sender
+    and commits them as `world` matrices of one height (same root: MMCS concatenates their rows)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n, wg = local_cols.rows, local_cols.width
     own_exch = exch is None
     if own_exch:
         exch = PeerExchange(ctx, n << added_bits, wg, group)
+    trace = os.environ.get("B200ZK_DIST_TRACE") == "1"   # experiments: host-clock phase times on rank 0 (adds synchronisation)
+    marks = []
+
+    def mark(what):
+        if trace:
+            torch.cuda.synchronize()
+            marks.append((what, time.perf_counter()))
     try:
+        mark("start")
         dist.barrier(group)            # every rank is done reading its receive buffer from the previous call
-        ctx.check(ctx.lib.b200zk_coset_lde_scatter(ctx.h, local_cols.h, added_bits, shift, world, rank, exch.ptr_array))
+        mark("barrier")
+        fn = ctx.lib.b200zk_coset_lde_scatter_rows if rows_layout else ctx.lib.b200zk_coset_lde_scatter
+        ctx.check(fn(ctx.h, local_cols.h, added_bits, shift, world, rank, exch.ptr_array))
         ctx.sync()                     # my stores (local and remote) are complete ...
+        mark("lde + scatter")
         dist.barrier(group)            # ... and so are everybody else's into my buffer
-        chunks = [exch.chunk(s) for s in range(world)]
-        arr = (C.c_void_p * world)(*[m.h for m in chunks])
+        mark("barrier")
+        chunks = [exch.matrix()] if rows_layout else [exch.chunk(s) for s in range(world)]
+        arr = (C.c_void_p * len(chunks))(*[m.h for m in chunks])
         root_local = np.empty(8, np.uint32)
         t = C.c_void_p()
-        ctx.check(ctx.lib.b200zk_merkle_commit(ctx.h, arr, world, 0, root_local.ctypes.data, C.byref(t)))
+        ctx.check(ctx.lib.b200zk_merkle_commit(ctx.h, arr, len(chunks), 0, root_local.ctypes.data, C.byref(t)))
         ctx.lib.b200zk_tree_free(ctx.h, t)
+        mark("subtree commit")
         dev = torch.device("cuda", ctx.device)
         cap_t = [torch.zeros(8, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(cap_t, torch.from_numpy(root_local.astype(np.int64)).to(dev), group=group)
         cap = np.stack([c.cpu().numpy().astype(np.uint32) for c in cap_t])
-        return combine_cap(cap, GpuOps(ctx).compress), cap
+        mark("cap all-gather")
+        root = combine_cap(cap, GpuOps(ctx).compress)
+        mark("top levels")
+        if trace and rank == 0:
+            print("[dist] " + "  ".join(f"{w} {1e3 * (b - a):.2f} ms" for (_, a), (w, b) in zip(marks, marks[1:])), flush=True)
+        return root, cap
     finally:
         if own_exch:
             exch.close()
