@@ -220,7 +220,10 @@ def test_coset_lde_fixture_kat(z, ctx, kats):
     assert np.array_equal(got, u32(k["lde_bitrev_rows"]))
 
 
-@pytest.mark.parametrize("n,w,b", [(0, 4, 1), (1, 3, 1), (3, 5, 2), (6, 32, 1), (9, 8, 1), (10, 36, 2), (12, 64, 1), (12, 7, 0), (13, 4, 3), (17, 8, 1), (19, 4, 1), (20, 4, 1)])
+# (15, 8, 1), (16, 8, 1), (16, 4, 2): two-pass plans whose fused middle runs K = 7 and K = 8 (the three-pass K = 7 / 8 middles are the
+# headline 2^23 and the 2^24 Horner tests); (7, 64, 1), (8, 32, 1): the whole LDE in the fused kernel alone
+@pytest.mark.parametrize("n,w,b", [(0, 4, 1), (1, 3, 1), (3, 5, 2), (6, 32, 1), (7, 64, 1), (8, 32, 1), (9, 8, 1), (10, 36, 2), (12, 64, 1), (12, 7, 0), (13, 4, 3),
+                                   (15, 8, 1), (16, 8, 1), (16, 4, 2), (17, 8, 1), (19, 4, 1), (20, 4, 1)])
 def test_coset_lde_matches_oracle(z, ctx, n, w, b):
     ev = rnd((1 << n, w), 200 + n + b)
     shift = int(O.to_monty([31])[0])
