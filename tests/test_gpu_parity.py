@@ -370,6 +370,22 @@ def test_pcs_commit_lde_plus_mmcs(z, ctx):
     pcs.mmcs.verify_batch(root, [(l.shape[1], l.shape[0]) for l in ldes], 1234, rows, path)
 
 
+def test_dft_algebra_variants_match_oracle(z, ctx):
+    """TwoAdicSubgroupDft::{dft, idft, coset_lde}_algebra_batch on EF4 inputs: the transform is F-linear, so every extension
+    coefficient column transforms like a base column (p3-dft flattens exactly this way); idft_algebra(dft_algebra(v)) == v"""
+    dft = z.B200Dft(ctx)
+    v = rnd((1 << 10, 3, 4), 77)                                    # 3 columns of EF4
+    flat = v.reshape(1 << 10, 12)
+    assert np.array_equal(dft.dft_algebra_batch(v).reshape(1 << 10, 12), O.dft_batch(flat))
+    assert np.array_equal(dft.idft_algebra_batch(dft.dft_algebra_batch(v)), v)
+    shift = int(O.to_monty([31])[0])
+    lde = dft.coset_lde_algebra_batch(v, 1, shift)
+    assert lde.shape == (1 << 11, 3, 4)
+    assert np.array_equal(lde.reshape(1 << 11, 12), O.coset_lde_batch(flat, 1, shift, bitrev_out=False))
+    one = rnd((64, 4), 78)                                           # a single EF4 vector (FRI's final polynomial path)
+    assert np.array_equal(dft.idft_algebra(dft.dft_algebra(one)), one)
+
+
 def test_commit_host_async_two_in_flight(z, ctx):
     """b200zk_lde_commit_host_async: commits issued back to back (two in flight, alternating strip buffers) give the roots
     of the blocking path, in any collection order, also when the shapes differ between calls (the strip buffers regrow)"""

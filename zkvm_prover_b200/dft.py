@@ -66,3 +66,47 @@ class B200Dft:
     def coset_lde(self, vec, added_bits: int, shift: int):
         import numpy as np
         return self.coset_lde_batch(np.asarray(vec, dtype=np.uint32).reshape(-1, 1), added_bits, shift).to_host().reshape(-1)
+
+    # ---- the *_algebra variants of the trait (extension-field inputs).  p3-dft implements them by flattening every extension
+    # element into its base coefficients (the transform is F-linear), transforming the `width * D` base columns and
+    # reconstituting; an EF4 matrix here is a (rows, width, 4) array or its (rows, 4 * width) flattening, so they are the
+    # base-field calls on the flattened view.  FRI's final polynomial (`idft_algebra` of the last folded vector) is the caller.
+    @staticmethod
+    def _flat(mat):
+        import numpy as np
+        a = np.ascontiguousarray(mat, dtype=np.uint32)
+        if a.ndim == 1:
+            raise ValueError("extension-field input needs a trailing axis of 4 coefficients")
+        shape = a.shape
+        return a.reshape(shape[0], -1), shape
+
+    def dft_algebra_batch(self, mat):
+        f, shape = self._flat(mat)
+        return self.dft_batch(f).to_host().reshape(shape)
+
+    def idft_algebra_batch(self, mat):
+        f, shape = self._flat(mat)
+        return self.idft_batch(f).to_host().reshape(shape)
+
+    def coset_dft_algebra_batch(self, mat, shift: int):
+        f, shape = self._flat(mat)
+        return self.coset_dft_batch(f, shift).to_host().reshape(shape)
+
+    def coset_idft_algebra_batch(self, mat, shift: int):
+        f, shape = self._flat(mat)
+        return self.coset_idft_batch(f, shift).to_host().reshape(shape)
+
+    def lde_algebra_batch(self, mat, added_bits: int):
+        f, shape = self._flat(mat)
+        return self.lde_batch(f, added_bits).to_host().reshape((shape[0] << added_bits,) + shape[1:])
+
+    def coset_lde_algebra_batch(self, mat, added_bits: int, shift: int):
+        f, shape = self._flat(mat)
+        return self.coset_lde_batch(f, added_bits, shift).to_host().reshape((shape[0] << added_bits,) + shape[1:])
+
+    def dft_algebra(self, vec):
+        """one vector of EF4 elements, shape (n, 4)"""
+        return self.dft_algebra_batch(vec)
+
+    def idft_algebra(self, vec):
+        return self.idft_algebra_batch(vec)
