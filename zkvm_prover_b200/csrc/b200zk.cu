@@ -844,15 +844,14 @@ int lde_core(b200zk_ctx* ctx, const uint32_t* src, uint32_t src_pitch, int n, ui
         std::vector<int> inv_plan = rest, fwd_plan = {km};
         inv_plan.push_back(km);
         fwd_plan.insert(fwd_plan.end(), rest.begin(), rest.end());
-        TRY(ensure_roots(ctx, n));
-        TRY(ensure_local(ctx, 0, km));
-        TRY(ensure_local(ctx, 1, km));
-        if (ctx->mid_sigma_pairs < C * R) return fail(ctx, B200ZK_ERR_ARG, "internal: lde_tables was not run for this shape");
+        int rc = ensure_roots(ctx, n);
+        if (rc == B200ZK_OK) rc = ensure_local(ctx, 0, km);
+        if (rc == B200ZK_OK) rc = ensure_local(ctx, 1, km);
+        if (rc == B200ZK_OK && ctx->mid_sigma_pairs < C * R) rc = fail(ctx, B200ZK_ERR_ARG, "internal: lde_tables was not run for this shape");
         ntt::MidParams mp{};
         const uint32_t* mid_in = src;
         uint32_t mid_pitch = src_pitch;
-        int rc = B200ZK_OK;
-        if (!rest.empty()) {
+        if (rc == B200ZK_OK && !rest.empty()) {
             uint32_t* work = scratch;
             uint32_t wpitch = scratch_pitch ? scratch_pitch : width;
             if (!work) {
