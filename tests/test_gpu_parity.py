@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI (ctypes) and the host mirror of the Plonky3
 traits, must be bit-identical to the oracle and to the golden vectors mined from the reference's fixture."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -368,6 +369,32 @@ def test_pcs_commit_lde_plus_mmcs(z, ctx):
         assert np.array_equal(pcs.get_evaluations_on_domain(pd, i).to_host(), l)
     rows, path = pcs.mmcs.open_batch(1234, pd)
     pcs.mmcs.verify_batch(root, [(l.shape[1], l.shape[0]) for l in ldes], 1234, rows, path)
+
+
+def test_unfused_lde_fallback_matches_fused(z, ctx):
+    """the unfused pass sequence (taken when the N x W scratch of the fused middle cannot be allocated, for n < 6 and for more than 8
+    cosets) stays bit-identical to the fused form: same LDE checksum and root from a child process run with B200ZK_LDE_FUSED_MID=0"""
+    import subprocess, sys, json
+    code = (
+        "import json, numpy as np, zkvm_prover_b200 as z\n"
+        "ctx = z.default_context(0)\n"
+        "rng = np.random.default_rng(4242)\n"
+        "out = []\n"
+        "for n, w, b in [(12, 64, 1), (15, 8, 2), (17, 12, 1)]:\n"
+        "    tr = rng.integers(0, z.P, (1 << n, w), dtype=np.uint64).astype(np.uint32)\n"
+        "    pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=b), ctx)\n"
+        "    root, pd = pcs.commit([tr])\n"
+        "    out.append([int(pd.mats[0].checksum()), [int(x) for x in root]])\n"
+        "print(json.dumps(out))\n"
+    )
+    env = dict(os.environ)
+    res = {}
+    for mode in ("1", "0"):
+        env["B200ZK_LDE_FUSED_MID"] = mode
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["1"] == res["0"]
 
 
 def test_dft_algebra_variants_match_oracle(z, ctx):
