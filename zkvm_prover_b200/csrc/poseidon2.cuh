@@ -213,11 +213,31 @@ BB_HD uint32_t div2(uint32_t x) {
     return ((x + MASK) >> K) + m * (15u << (27 - K));
 }
 #define P2_SUM_ADD(lvl, a, b) ((P2_INT_SUM_FMA >= (lvl)) ? add_f((a), (b)) : bb::add((a), (b)))
+#ifndef P2_INT_SUM_WIDE
+#define P2_INT_SUM_WIDE 0  // experiment: 1 = the 16-lane sum in a 64-bit accumulator (8 plain pair sums + 7 IMAD.WIDE + one reduction: 21 instructions instead of 30)
+#endif
+#if P2_INT_SUM_WIDE
+BB_HD uint32_t sum16(const uint32_t (&s)[16]) {
+    uint64_t acc = (uint64_t)(s[0] + s[1]);
+    acc = bb::fadd64(acc, s[2] + s[3]);
+    acc = bb::fadd64(acc, s[4] + s[5]);
+    acc = bb::fadd64(acc, s[6] + s[7]);
+    uint64_t acc2 = (uint64_t)(s[8] + s[9]);
+    acc2 = bb::fadd64(acc2, s[10] + s[11]);
+    acc2 = bb::fadd64(acc2, s[12] + s[13]);
+    acc2 = bb::fadd64(acc2, s[14] + s[15]);
+    acc += acc2;
+    uint32_t q = (uint32_t)(acc >> 31);          // < 32
+    uint32_t r = (uint32_t)acc - q * bb::P;      // < 2^31 + 31 * 2^27 < 2^32
+    return bb::red2p(bb::red2p(r));              // r < 2^32 < 2.14 p
+}
+#else
 BB_HD uint32_t sum16(const uint32_t (&s)[16]) {
     uint32_t a0 = P2_SUM_ADD(1, s[0], s[1]), a1 = P2_SUM_ADD(1, s[2], s[3]), a2 = P2_SUM_ADD(1, s[4], s[5]), a3 = P2_SUM_ADD(1, s[6], s[7]);
     uint32_t a4 = P2_SUM_ADD(1, s[8], s[9]), a5 = P2_SUM_ADD(1, s[10], s[11]), a6 = P2_SUM_ADD(1, s[12], s[13]), a7 = P2_SUM_ADD(1, s[14], s[15]);
     return P2_SUM_ADD(3, P2_SUM_ADD(2, P2_SUM_ADD(2, a0, a1), P2_SUM_ADD(2, a2, a3)), P2_SUM_ADD(2, P2_SUM_ADD(2, a4, a5), P2_SUM_ADD(2, a6, a7)));
 }
+#endif
 #endif
 
 #define P2_OUT_ADD(lvl, a, b) ((P2_INT_OUT_FMA >= (lvl)) ? add_f((a), (b)) : bb::add((a), (b)))
