@@ -299,11 +299,12 @@ def main():
     leaf_bytes = 4 * m_rows * w + 32 * m_rows
     peak, peak_src = peaks()
     perms = m_rows * ((w + 7) // 8)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, lde_traffic = None, None, None
     try:  # DRAM bytes per launch of this kernel: one `ncu --set full` capture of this same command (profiles/, per round)
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         if args.log_rows == 23 and w == 256 and b == 1:
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source", "profiles/roofline_traffic.json (ncu --set full capture of this workload)")
+            lde_traffic = tj.get("lde_dram_bytes_per_step")
     except Exception:
         pass
     gperm = perms / (leaf_ms * 1e-3) / 1e9
@@ -320,7 +321,8 @@ def main():
                 "peak_int_source": "564 products x 10 FMA-heavy-pipe clocks per warp-permutation at the SM clock sampled during the run (pipe rates measured in profiles/pipe_microbench_r01.txt)",
                 "note": "achieved/peak/frac are the HBM view the bench contract asks for; the kernel is bound by the 32-bit integer pipes (frac_int), its DRAM traffic equals its algorithmic bytes",
                 "lde": {"ms": round(lde_ms, 3), "achieved": round(b_lde / (lde_ms * 1e-3) / 1e9, 2), "frac": round(b_lde / (lde_ms * 1e-3) / 1e9 / peak, 4),
-                        "bound": "hbm+int32", "note": "6 pass sweeps of 8 B per element + the fused middle (4 B read + 8 B written per element); per-pass times in profiles/ntt_fused_mid_r02.txt, copy-only ceilings of the tile shapes in profiles/tile_copy_lab_r02.txt"},
+                        "bound": "hbm+int32", "traffic": lde_traffic, "dram_frac": (round(lde_traffic / (lde_ms * 1e-3) / 1e9 / peak, 4) if lde_traffic else None),
+                        "note": "traffic = DRAM bytes of the 7 LDE launches of a step (ncu, profiles/ncu_summary_r02.json), dram_frac = traffic / time / peak; 6 pass sweeps of 8 B per element + the fused middle (4 B read + 8 B written per element); per-pass times in profiles/ntt_fused_mid_r02.txt, copy-only ceilings of the tile shapes in profiles/tile_copy_lab_r02.txt"},
                 "commit_ms": round(commit_ms, 3)}
 
     # ---- e2e: host buffers through the C ABI (pinned trace -> H2D -> LDE -> commit -> root D2H)
