@@ -117,7 +117,8 @@ int b200zk_lde_commit(b200zk_ctx*, b200zk_mat* const* evals, uint32_t k, uint32_
 /* the same for ONE trace that still lives in host memory (pinned for full speed): the matrix is processed in column
  * strips so the host->device transfer of strip s+1 overlaps the LDE and leaf hashing of strip s (copy stream + compute
  * stream).  strip_cols = 0 picks the strip width (32 columns; 64 for the asynchronous form below, where only the copy rate
- * matters).  Small or ragged inputs take the plain upload path.  Bit-identical to b200zk_mat_upload + b200zk_lde_commit. */
+ * matters).  Small or ragged inputs take the plain upload path.  Bit-identical to b200zk_mat_upload + b200zk_lde_commit.
+ * The context keeps its four strip buffers (rows x strip columns each) for the next call; b200zk_ctx_trim releases them. */
 int b200zk_lde_commit_host(b200zk_ctx*, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits,
                            uint32_t shift_monty, uint32_t strip_cols, uint32_t h_root[8], b200zk_tree** out);
 /* the same without waiting: returns once every copy and kernel is enqueued.  h_values must stay valid (and unmodified) until
