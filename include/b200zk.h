@@ -122,7 +122,8 @@ int b200zk_lde_commit(b200zk_ctx*, b200zk_mat* const* evals, uint32_t k, uint32_
 int b200zk_lde_commit_host(b200zk_ctx*, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits,
                            uint32_t shift_monty, uint32_t strip_cols, uint32_t h_root[8], b200zk_tree** out);
 /* the same without waiting: returns once every copy and kernel is enqueued.  h_values must stay valid (and unmodified) until
- * b200zk_tree_root(tree) or b200zk_ctx_sync returns.  Two calls may be in flight per context (their strip buffers alternate):
+ * b200zk_tree_root(tree) or b200zk_ctx_sync returns (collect a root before 64 further asynchronous commits are issued: the pinned
+ * slots the roots land in are recycled).  Two calls may be in flight per context (their strip buffers alternate):
  * issuing call i+1 before reading the root of call i hides the first strip's transfer under the previous call's arithmetic
  * -- how a prover walks the segments of a chunk proof (crates/prover/src/prover/mod.rs:355-357 proves them one after another). */
 int b200zk_lde_commit_host_async(b200zk_ctx*, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits,

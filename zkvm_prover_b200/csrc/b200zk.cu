@@ -76,8 +76,10 @@ struct b200zk_tree {
     mk::OpenMat* d_open = nullptr;
     // asynchronous commits (b200zk_lde_commit_host_async): the root is copied to a pinned slot behind the last kernel and
     // `ev_done` marks that point, so b200zk_tree_root waits for THIS tree only, not for commits enqueued after it
-    cudaEvent_t ev_done = nullptr;
-    uint32_t* h_root_slot = nullptr;
+    mutable cudaEvent_t ev_done = nullptr;
+    mutable uint32_t* h_root_slot = nullptr;   // one of 64 pinned slots of the context: valid until 64 later asynchronous commits were issued
+    mutable uint32_t root_cache[8] = {};       // the root, once collected (the slot is recycled)
+    mutable bool root_cached = false;
 };
 struct b200zk_chal {
     fri::ChalState* d = nullptr;
@@ -1301,9 +1303,18 @@ static int commit_async(b200zk_ctx* ctx, b200zk_mat* const* mats, uint32_t k, in
 int b200zk_tree_root(b200zk_ctx* ctx, const b200zk_tree* t, uint32_t h_root[8]) {
     if (!ctx) return B200ZK_ERR_ARG;
     if (!t || !h_root) return fail(ctx, B200ZK_ERR_ARG, "null tree/root");
-    if (t->ev_done) {  // asynchronous commit: wait for this tree's own completion point
+    if (t->root_cached) {
+        memcpy(h_root, t->root_cache, 32);
+        return B200ZK_OK;
+    }
+    if (t->ev_done) {  // asynchronous commit: wait for this tree's own completion point, then keep the root (the pinned slot is recycled)
         CU(cudaEventSynchronize(t->ev_done));
-        memcpy(h_root, t->h_root_slot, 32);
+        memcpy(t->root_cache, t->h_root_slot, 32);
+        t->root_cached = true;
+        cudaEventDestroy(t->ev_done);
+        t->ev_done = nullptr;
+        t->h_root_slot = nullptr;
+        memcpy(h_root, t->root_cache, 32);
         return B200ZK_OK;
     }
     CU(cudaMemcpyAsync(h_root, t->d_digests + 8 * (2 * t->max_h - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
