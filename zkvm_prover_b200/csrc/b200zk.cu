@@ -397,11 +397,15 @@ int run_transform(b200zk_ctx* ctx, const uint32_t* src, uint32_t* work, uint32_t
             p.prefetch_dist = e ? (uint32_t)atoi(e) : 148u; // measured best look-ahead of pass_kernel (profiles/ntt_tuning_r01.txt)
         }
         const uint64_t R = 1ull << K;
-        // Passes that multiply by per-row factors (coset prescale, inter-pass twist: every pass but the last one of a
-        // transform) run on the direct kernel, which computes the factor tables under its own global loads (B200, LDE
-        // 2^23 x 256: 4.75 / 4.55 / 5.2 ms per pass against 5.0 / 4.9 / 6.3 ms on the TMA ring); the factor-free last pass
-        // stays on the TMA ring (3.8 against 4.1-4.4 ms).  profiles/ntt_lab_r02.txt
-        const bool has_factors = p.pre_lo != nullptr || (n - s0 - K) > 0;
+        // Passes of K = 6..8 stages run on the direct kernel (B200, LDE 2^23 x 256: 4.75 / 4.55 / 5.2 ms per pass with factors
+        // against 5.0 / 4.9 / 6.3 ms on the TMA ring, profiles/ntt_lab_r02.txt; the factor-free K = 8 last pass 3.64 against
+        // 4.16 ms, profiles/ntt_fused_mid_r02.txt).  The TMA ring keeps the other K, the natural-order scatter of the unfused
+        // inverse and the peer-memory scatter of the sharded LDE.
+        static const bool direct_last = [] {
+            const char* e = getenv("B200ZK_DIRECT_LAST");  // experiment knob: 0 = the factor-free last pass back on the TMA ring
+            return !e || atoi(e) != 0;                     // measured r02, K = 8 last pass at 2^23 x 256: direct 3.64 ms, TMA ring 4.16 ms
+        }();
+        const bool has_factors = p.pre_lo != nullptr || (n - s0 - K) > 0 || (direct_last && !p.out_natural);
         if (tma_ok && direct_enabled() && has_factors && K >= 6 && K <= 8 && !p.post_lo && !(last && scatter)) {
             // direct pass: 2^13-element tiles, first round from global memory, last round to global memory (ntt.cuh)
             const int lcd = 13 - K;
