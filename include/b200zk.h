@@ -128,6 +128,11 @@ int b200zk_lde_commit_host(b200zk_ctx*, const uint32_t* h_values, uint64_t rows,
  * -- how a prover walks the segments of a chunk proof (crates/prover/src/prover/mod.rs:355-357 proves them one after another). */
 int b200zk_lde_commit_host_async(b200zk_ctx*, const uint32_t* h_values, uint64_t rows, uint32_t width, uint32_t added_bits,
                                  uint32_t shift_monty, uint32_t strip_cols, b200zk_tree** out);
+/* page-locked host memory for traces handed to the two calls above (any page-locked or pageable memory works; this is the fast kind).
+ * write_combined = 1: write-combining pages -- fill them with plain stores, do not read them back on the CPU; device reads do not
+ * snoop the CPU caches (helps when several GPUs pull from host memory at once). */
+int b200zk_host_alloc(uint64_t bytes, int write_combined, void** h_out);
+void b200zk_host_free(void* h);
 /* Mmcs::open_batch(index): rows_out = concatenation over matrices (original order) of row
  * index >> (log2 max_height - log2 height); path_out = depth x 8 siblings, bottom-up */
 int b200zk_merkle_open(b200zk_ctx*, const b200zk_tree*, uint64_t index, uint32_t* h_rows, uint32_t* h_path);

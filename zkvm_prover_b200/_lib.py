@@ -71,6 +71,8 @@ _SIGS = {
     "b200zk_lde_commit": (_int, [_p, C.POINTER(_p), _u32, _u32, _p, _p, C.POINTER(_p)]),
     "b200zk_lde_commit_host": (_int, [_p, _p, _u64, _u32, _u32, _u32, _u32, _p, C.POINTER(_p)]),
     "b200zk_lde_commit_host_async": (_int, [_p, _p, _u64, _u32, _u32, _u32, _u32, C.POINTER(_p)]),
+    "b200zk_host_alloc": (_int, [_u64, _int, C.POINTER(_p)]),
+    "b200zk_host_free": (None, [_p]),
     "b200zk_merkle_open": (_int, [_p, _p, _u64, _p, _p]),
     "b200zk_merkle_open_many": (_int, [_p, _p, _p, _u32, _p, _p]),
     "b200zk_tree_depth": (_u32, [_p]),

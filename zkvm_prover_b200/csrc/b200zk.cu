@@ -2247,6 +2247,25 @@ int b200zk_coset_lde_scatter_rows(b200zk_ctx* ctx, const b200zk_mat* evals, uint
     return lde_scatter_impl(ctx, evals, added_bits, shift, world, rank, d_recv, true);
 }
 
+// ================================================================================================ host staging memory
+// Page-locked host memory for traces that will be committed with b200zk_lde_commit_host(_async).  write_combined = 1 asks for
+// write-combining pages: the CPU fills them with streaming stores (reading them back on the CPU is slow) and the device's DMA reads do
+// not snoop the CPU caches, which matters when several GPUs pull from host memory at once.
+int b200zk_host_alloc(uint64_t bytes, int write_combined, void** h_out) {
+    if (!h_out) return B200ZK_ERR_ARG;
+    *h_out = nullptr;
+    cudaError_t e = cudaHostAlloc(h_out, bytes ? bytes : 16, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *h_out = nullptr;
+        return e == cudaErrorMemoryAllocation ? B200ZK_ERR_OOM : B200ZK_ERR_CUDA;
+    }
+    return B200ZK_OK;
+}
+void b200zk_host_free(void* h) {
+    if (h) cudaFreeHost(h);
+}
+
 // ================================================================================================ raw memory
 int b200zk_dev_alloc(b200zk_ctx* ctx, uint64_t bytes, void** d_out) {
     if (!ctx || !d_out) return B200ZK_ERR_ARG;
