@@ -58,6 +58,11 @@ lh = summary.get(f"leaf_hash_{R}")
 if lh:
     def num(s): return float(s.split()[0].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[s.split()[1]]
     t = num(lh[0]["dram__bytes_read.sum"]) + num(lh[0]["dram__bytes_write.sum"])
-    json.dump({"kernel": "mk::leaf_hash_fast_kernel", "round": R, "dram_bytes_per_launch": t, "source": f"profiles/ncu_summary_{R}.json"},
-              open(os.path.join(PR, "roofline_traffic.json"), "w"))
+    out = {"kernel": "mk::leaf_hash_fast_kernel", "round": R, "dram_bytes_per_launch": t, "source": f"profiles/ncu_summary_{R}.json"}
+    ntt = summary.get(f"ntt_passes_{R}")
+    if ntt:  # the LDE launches of one step (capture_profiles.sh captures exactly one step's worth)
+        out["lde_dram_bytes_per_step"] = sum(num(e["dram__bytes_read.sum"]) + num(e["dram__bytes_write.sum"]) for e in ntt)
+        out["lde_source"] = f"profiles/ncu_summary_{R}.json (the {len(ntt)} LDE launches of one step, ncu --set full)"
+        print("LDE DRAM traffic per step:", out["lde_dram_bytes_per_step"] / 1e9, "GB")
+    json.dump(out, open(os.path.join(PR, "roofline_traffic.json"), "w"))
     print("leaf hash DRAM traffic per launch:", t / 1e9, "GB")
