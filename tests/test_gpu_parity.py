@@ -371,6 +371,41 @@ def test_pcs_commit_lde_plus_mmcs(z, ctx):
     pcs.mmcs.verify_batch(root, [(l.shape[1], l.shape[0]) for l in ldes], 1234, rows, path)
 
 
+def test_host_commit_async_errors_and_staging_memory(z, ctx):
+    """error behaviour of b200zk_lde_commit_host_async (same argument checks as the blocking call, nothing left enqueued), and a
+    trace staged in b200zk_host_alloc memory (write-combined) commits to the same root; the root of an asynchronous commit can be
+    collected more than once"""
+    lib = ctx.lib
+    t = C.c_void_p()
+    good = np.ascontiguousarray(rnd((1 << 12, 64), 31))
+    shift = z.GENERATOR_MONTY
+    rc = lib.b200zk_lde_commit_host_async(ctx.h, None, 1 << 12, 64, 1, shift, 0, C.byref(t))
+    assert rc != 0 and not t.value
+    rc = lib.b200zk_lde_commit_host_async(ctx.h, good.ctypes.data, 3000, 64, 1, shift, 0, C.byref(t))       # not a power of two
+    assert rc != 0 and not t.value
+    rc = lib.b200zk_lde_commit_host_async(ctx.h, good.ctypes.data, 1 << 12, 64, 1, 0, 0, C.byref(t))         # shift 0
+    assert rc != 0 and not t.value
+    # staging memory
+    hp = C.c_void_p()
+    big = np.ascontiguousarray(rnd((1 << 16, 64), 32))                                                      # 2^22 elements: takes the strip pipeline
+    ctx.check(lib.b200zk_host_alloc(big.nbytes, 1, C.byref(hp)))
+    try:
+        C.memmove(hp.value, big.ctypes.data, big.nbytes)
+        pcs = z.TwoAdicFriPcs(z.FriConfig(log_blowup=1), ctx)
+        want, pd = pcs.commit([big])
+        pd.free()
+        pend = pcs.commit_host_async(hp.value, big.shape)
+        r1 = np.empty(8, np.uint32)
+        r2 = np.empty(8, np.uint32)
+        ctx.check(lib.b200zk_tree_root(ctx.h, pend.tree, r1.ctypes.data))
+        ctx.check(lib.b200zk_tree_root(ctx.h, pend.tree, r2.ctypes.data))
+        lib.b200zk_tree_free(ctx.h, pend.tree)
+        assert np.array_equal(r1, want) and np.array_equal(r2, want)
+    finally:
+        lib.b200zk_host_free(hp)
+    assert lib.b200zk_host_alloc(16, 0, None) != 0
+
+
 def test_unfused_lde_fallback_matches_fused(z, ctx):
     """the unfused pass sequence (taken when the N x W scratch of the fused middle cannot be allocated, for n < 6 and for more than 8
     cosets) stays bit-identical to the fused form: same LDE checksum and root from a child process run with B200ZK_LDE_FUSED_MID=0"""
