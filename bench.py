@@ -377,8 +377,13 @@ def main():
         root_dev = root.copy()
         serial_ms = timed(run_serial)
         assert np.array_equal(root, root_dev), "host strip pipeline: root differs from the device-resident path"
-        stream_ms = timed(run_stream, warm=max(3, args.warmup))
-        assert np.array_equal(root, root_dev), "host strip pipeline (async): root differs from the device-resident path"
+        stream_note = None
+        try:
+            stream_ms = timed(run_stream, warm=max(3, args.warmup))
+            assert np.array_equal(root, root_dev), "host strip pipeline (async): root differs from the device-resident path"
+        except z.B200zkError as ex:  # e.g. no room for two commits in flight: report the blocking number as the e2e value
+            ctx.sync()
+            stream_ms, stream_note = serial_ms, f"streamed mode failed ({ex}); value is the blocking call's"
         e_ms = torch.tensor([stream_ms], device="cuda")
         # what the host link gives every rank when all ranks copy at once: a plain contiguous pinned H2D copy (2 GiB), all
         # ranks together -- the bound of any e2e number at this N (the GPUs of one box share host memory and PCIe uplinks)
@@ -399,7 +404,7 @@ def main():
         link_gbs = float(link.item())
         e2e = {"value": round(world * (b_lde + b_commit) / (float(e_ms.item()) * 1e-3) / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": 4 * n * w, "d2h_bytes_per_step": 32,
                "ms_per_step": round(float(e_ms.item()), 3), "strip_cols": strip_cols or 64,
-               "mode": "stream of K commits through b200zk_lde_commit_host_async, at most two in flight; every commit's H2D and root D2H inside the timed region",
+               "mode": stream_note or "stream of K commits through b200zk_lde_commit_host_async, at most two in flight; every commit's H2D and root D2H inside the timed region",
                "serial": {"value": round(world * (b_lde + b_commit) / (serial_ms * 1e-3) / 1e9, 3), "ms_per_step": round(serial_ms, 3), "strip_cols": strip_cols or 32,
                           "mode": "one blocking b200zk_lde_commit_host call at a time"},
                "h2d_link_gbs_per_gpu": round(link_gbs, 1), "h2d_floor_ms": round(4 * n * w / link_gbs / 1e6, 1),
